@@ -1,0 +1,174 @@
+/*
+ * shoulder_b200.h — C ABI of the B200 (sm_100a) multiplane slicing / unrolling backend.
+ *
+ * Drop-in boundary for ONE path of gregspangenberg/shoulder: the `Slices` provider
+ * (reference src/shoulder/humerus/slice.py:9-207).  The reference has no FFI of its own for
+ * this path — it makes one Python call into trimesh,
+ *
+ *     self.obb.mesh.section_multiplane(plane_origin=[0,0,z_orig], plane_normal=[0,0,1],
+ *                                      heights=z_incrs)            (slice.py:24-28)
+ *
+ * and then loops over the returned Path2D objects (slice.py:34-147).  The entry points below
+ * are what a ctypes binding for that path needs; each cites the reference code it replaces.
+ * Plain pointers and sizes only; no torch / numpy types.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SHB_E_* code; shb_last_error() gives
+ *     the thread-local message.  Nothing throws across the boundary.
+ *   - inputs are caller-owned and only borrowed for the duration of the call.
+ *   - results are backend-owned; arrays returned by shb_result_array() are pinned host
+ *     buffers valid until shb_result_free().
+ *   - per-plane anomalies (no intersection, open contour, non-manifold node) are DATA
+ *     (SHB_ARR_STATUS bits), not errors — trimesh returns None / odd paths there too.
+ *   - there is no CPU fallback: without a CUDA device every call fails with SHB_E_CUDA.
+ */
+#ifndef SHOULDER_B200_H
+#define SHOULDER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHB_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SHB_API __attribute__((visibility("default")))
+#else
+#define SHB_API
+#endif
+
+/* error codes */
+#define SHB_OK            0
+#define SHB_E_INVALID    -1   /* bad argument (null pointer, negative size, index out of range) */
+#define SHB_E_CUDA       -2   /* CUDA runtime error, or no device */
+#define SHB_E_NOMEM      -3
+#define SHB_E_CAPACITY   -4   /* a 32-bit internal index would overflow; split the batch */
+#define SHB_E_STATE      -5   /* array not computed (not in outputs_mask) / bad handle */
+
+/* outputs_mask bits: which arrays shb_batch_run computes / shb_sweep_batch brings to the host */
+#define SHB_OUT_PLANE              0x001u  /* always on: n_seg, n_entities, status, bounds, centroid, area1 */
+#define SHB_OUT_SEGMENTS           0x002u  /* mesh_multiplane's lines_2D + face_index          */
+#define SHB_OUT_CONTOURS           0x004u  /* Path2D.discrete of every closed entity + areas   */
+#define SHB_OUT_IXY                0x008u  /* slice.py:65-80   */
+#define SHB_OUT_IXY_CENTERED       0x010u  /* slice.py:85-87   */
+#define SHB_OUT_ITR                0x020u  /* slice.py:92-97   (theta-sorted polar)            */
+#define SHB_OUT_ITR_START          0x040u  /* slice.py:102-108 (polar rolled to argmin theta)  */
+#define SHB_OUT_ITR_CENTERED       0x080u  /* slice.py:124-134 */
+#define SHB_OUT_ITR_CENTERED_START 0x100u  /* slice.py:136-144 */
+#define SHB_OUT_RADIAL             0x200u  /* extra product: ray-cast radius image, n_angles per plane */
+#define SHB_OUT_ALL_PROFILES       0x1F8u
+
+/* array ids for shb_result_array */
+enum shb_array {
+    SHB_ARR_N_SEG = 0,        /* int32  [P]        segments on the plane                                */
+    SHB_ARR_SEG_OFF,          /* int64  [P+1]      offset of the plane's segments, sweep-relative       */
+    SHB_ARR_N_ENT,            /* int32  [P]        len(Path2D.entities)                    slice.py:53,70 */
+    SHB_ARR_STATUS,           /* uint32 [P]        SHB_ST_* bits                                         */
+    SHB_ARR_BOUNDS,           /* f64    [P,2,2]    Path2D.bounds                                         */
+    SHB_ARR_CENTROID,         /* f64    [P,2]      Path2D.centroid                         slice.py:34-39 */
+    SHB_ARR_AREA1,            /* f64    [P]        slice.py:49-60 for planes with one shell (see DESIGN) */
+    SHB_ARR_SEL,              /* int32  [P,2]      (contour id, point count) of the outline ixy uses     */
+    SHB_ARR_FACE_INDEX,       /* int32  [S]        metadata['face_index'], basic|vertex|edge, ascending  */
+    SHB_ARR_SEGMENTS,         /* f64    [S,2,2]    lines_2D                                              */
+    SHB_ARR_CONTOUR_OFF,      /* int64  [P+1]      first contour of each plane, sweep-relative           */
+    SHB_ARR_CONTOUR_PT_OFF,   /* int64  [C+1]      first point of each contour in POINTS                 */
+    SHB_ARR_CONTOUR_AREA,     /* f64    [C]        |area| of each closed polygon            slice.py:55-57 */
+    SHB_ARR_POINTS,           /* f64    [Npts,2]   Path2D.discrete, CCW, closed (first == last)          */
+    SHB_ARR_IXY,              /* f64    [P,2,N] */
+    SHB_ARR_IXY_CENTERED,     /* f64    [P,2,N] */
+    SHB_ARR_ITR,              /* f64    [P,2,N] */
+    SHB_ARR_ITR_START,        /* f64    [P,2,N] */
+    SHB_ARR_ITR_CENTERED,     /* f64    [P,2,N] */
+    SHB_ARR_ITR_CENTERED_START,/* f64   [P,2,N] */
+    SHB_ARR_RADIAL,           /* f64    [P,A]   */
+    SHB_ARR_COUNT
+};
+
+/* dtype codes written by shb_result_array */
+#define SHB_DT_I32 1
+#define SHB_DT_I64 2
+#define SHB_DT_U32 3
+#define SHB_DT_F64 4
+
+/* per-plane status bits */
+#define SHB_ST_EMPTY        0x01u  /* no face crosses the plane: section_multiplane yields None   */
+#define SHB_ST_OPEN         0x02u  /* some contour does not close (mesh not watertight there)      */
+#define SHB_ST_NONMANIFOLD  0x04u  /* a node has more than two incident segments                   */
+#define SHB_ST_RANK_TIE     0x08u  /* two distinct nodes share a rounded-coordinate hash (H4-i)    */
+#define SHB_ST_SPLIT_COPY   0x10u  /* two copies of one node round differently (H4-ii)             */
+#define SHB_ST_GENERAL      0x20u  /* plane was stitched by the general (serial DFS) path          */
+
+typedef struct shb_batch  shb_batch;
+typedef struct shb_result shb_result;
+
+/* Library / device bring-up.  device = CUDA ordinal for this process (one process per GPU).
+ * Idempotent.  Replaces nothing in the reference (it is CPU-only). */
+SHB_API int shb_init(int device);
+
+/* Kernels are enqueued on this stream (a cudaStream_t; NULL = the library's own stream). */
+SHB_API int shb_set_stream(void* cuda_stream);
+
+/* Upload a batch of meshes and the sweeps to run on them; inputs become HBM-resident.
+ *   verts  (sum V,3) f64 OBB-frame vertices, meshes concatenated; vert_off [n_mesh+1]
+ *   faces  (sum T,3) i64 mesh-local vertex ids (as trimesh holds them); face_off [n_mesh+1]
+ *   sweep k slices mesh sweep_mesh[k] with the planes  z = z_orig[k] + heights[height_off[k] .. height_off[k+1])
+ *   and resamples each outline to interp_num[k] points.
+ * Replaces the argument set of slice.py:24-28 plus Slices.__init__ (slice.py:10-19). */
+SHB_API int shb_batch_create(int32_t n_mesh,
+                     const double* verts, const int64_t* vert_off,
+                     const int64_t* faces, const int64_t* face_off,
+                     int32_t n_sweep, const int32_t* sweep_mesh,
+                     const double* z_orig,
+                     const double* heights, const int64_t* height_off,
+                     const int32_t* interp_num,
+                     shb_batch** out);
+SHB_API int shb_batch_free(shb_batch* batch);
+
+/* Run the whole hot path on the device for every sweep of the batch: bucket -> intersect ->
+ * stitch -> resample/unroll.  Results stay on the device until fetched.
+ * Replaces slice.py:21-29 (_slices) and the loops of slice.py:34-147. */
+SHB_API int shb_batch_run(shb_batch* batch, uint32_t outputs_mask, int32_t n_angles, shb_result** out);
+
+/* One-call form with host buffers in and out (create + run + fetch of outputs_mask + free). */
+SHB_API int shb_sweep_batch(int32_t n_mesh,
+                    const double* verts, const int64_t* vert_off,
+                    const int64_t* faces, const int64_t* face_off,
+                    int32_t n_sweep, const int32_t* sweep_mesh,
+                    const double* z_orig,
+                    const double* heights, const int64_t* height_off,
+                    const int32_t* interp_num,
+                    uint32_t outputs_mask, int32_t n_angles,
+                    shb_result** out);
+
+/* Bring the arrays selected by `mask` to pinned host memory (device -> host copy + sync). */
+SHB_API int shb_result_fetch(shb_result* result, uint32_t mask);
+
+/* Borrow one array of one sweep.  shape[0..ndim) is filled, *dtype gets a SHB_DT_* code.
+ * Returns NULL (and sets the error) if the array was not computed; fetches it if needed. */
+SHB_API const void* shb_result_array(shb_result* result, int32_t which, int32_t sweep,
+                             int64_t shape[4], int32_t* ndim, int32_t* dtype);
+
+/* Totals of a result: planes, segments, contours, points; device milliseconds per stage of the
+ * last run when profiling is enabled (stage order: bucket, scan, scatter, intersect, scan2,
+ * stitch, resample).  Any pointer may be NULL. */
+SHB_API int shb_result_totals(const shb_result* result, int64_t* n_plane, int64_t* n_seg,
+                      int64_t* n_contour, int64_t* n_point);
+SHB_API int shb_result_free(shb_result* result);
+
+/* Per-stage CUDA-event timing of shb_batch_run (adds one event pair per stage). */
+#define SHB_N_STAGES 7
+SHB_API int shb_profile_enable(int on);
+SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launches[SHB_N_STAGES], int reset);
+
+/* Number of kernels this library has launched since shb_init (bench.py's gpu_launches). */
+SHB_API int64_t shb_launch_count(void);
+
+SHB_API const char* shb_last_error(void);
+SHB_API int shb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHOULDER_B200_H */

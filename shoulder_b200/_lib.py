@@ -1,0 +1,220 @@
+"""ctypes binding of ``libshoulder_b200.so`` (C ABI: ``include/shoulder_b200.h``).
+
+The library is the product; there is no Python or CPU fallback.  Loading fails loudly when the
+shared object is missing, and ``init()`` fails loudly when there is no sm_100 device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+LIB_PATH = Path(__file__).resolve().parent / "libshoulder_b200.so"
+
+# --- constants mirrored from include/shoulder_b200.h ---------------------------------------
+ABI_VERSION = 1
+OUT_PLANE, OUT_SEGMENTS, OUT_CONTOURS = 0x001, 0x002, 0x004
+OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START = 0x008, 0x010, 0x020, 0x040
+OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL = 0x080, 0x100, 0x200
+OUT_ALL_PROFILES = 0x1F8
+(ARR_N_SEG, ARR_SEG_OFF, ARR_N_ENT, ARR_STATUS, ARR_BOUNDS, ARR_CENTROID, ARR_AREA1, ARR_SEL, ARR_FACE_INDEX,
+ ARR_SEGMENTS, ARR_CONTOUR_OFF, ARR_CONTOUR_PT_OFF, ARR_CONTOUR_AREA, ARR_POINTS, ARR_IXY, ARR_IXY_CENTERED, ARR_ITR,
+ ARR_ITR_START, ARR_ITR_CENTERED, ARR_ITR_CENTERED_START, ARR_RADIAL, ARR_COUNT) = range(22)
+ST_EMPTY, ST_OPEN, ST_NONMANIFOLD, ST_RANK_TIE, ST_SPLIT_COPY, ST_GENERAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+N_STAGES = 7
+STAGE_NAMES = ("bucket", "scan", "scatter", "intersect", "scan2", "stitch", "resample")
+_DTYPES = {1: np.int32, 2: np.int64, 3: np.uint32, 4: np.float64}
+
+EXPORTS = (
+    "shb_init", "shb_set_stream", "shb_batch_create", "shb_batch_free", "shb_batch_run", "shb_sweep_batch",
+    "shb_result_fetch", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
+    "shb_profile_read", "shb_launch_count", "shb_last_error", "shb_abi_version",
+)
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the CUDA library (no device needed for this step)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise BackendError(
+            f"{LIB_PATH} is missing: build it with `python -m shoulder_b200.build` (needs nvcc). "
+            "shoulder_b200 has no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    p, i32, i64, u32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32
+    pp = C.POINTER(C.c_void_p)
+    lib.shb_init.argtypes = [C.c_int]
+    lib.shb_set_stream.argtypes = [p]
+    lib.shb_batch_create.argtypes = [i32, p, p, p, p, i32, p, p, p, p, p, pp]
+    lib.shb_batch_free.argtypes = [p]
+    lib.shb_batch_run.argtypes = [p, u32, i32, pp]
+    lib.shb_sweep_batch.argtypes = [i32, p, p, p, p, i32, p, p, p, p, p, u32, i32, pp]
+    lib.shb_result_fetch.argtypes = [p, u32]
+    lib.shb_result_array.argtypes = [p, i32, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
+    lib.shb_result_array.restype = C.c_void_p
+    lib.shb_result_totals.argtypes = [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    lib.shb_result_free.argtypes = [p]
+    lib.shb_profile_enable.argtypes = [C.c_int]
+    lib.shb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
+    lib.shb_launch_count.restype = i64
+    lib.shb_last_error.restype = C.c_char_p
+    for name in EXPORTS:
+        if name not in ("shb_result_array", "shb_launch_count", "shb_last_error"):
+            getattr(lib, name).restype = C.c_int
+    if lib.shb_abi_version() != ABI_VERSION:
+        raise BackendError("libshoulder_b200.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise BackendError(f"shoulder_b200 error {rc}: {load().shb_last_error().decode()}")
+
+
+_inited = None
+
+
+def init(device: int = 0) -> None:
+    """Bring the device up.  Raises if there is no sm_100 GPU — nothing runs on the CPU."""
+    global _inited
+    if _inited == device:
+        return
+    check(load().shb_init(int(device)))
+    _inited = device
+
+
+def set_stream(stream_ptr: int | None) -> None:
+    check(load().shb_set_stream(C.c_void_p(stream_ptr or 0)))
+
+
+def profile_enable(on: bool) -> None:
+    check(load().shb_profile_enable(1 if on else 0))
+
+
+def profile_read(reset: bool = True):
+    ms = (C.c_double * N_STAGES)()
+    n = (C.c_int64 * N_STAGES)()
+    check(load().shb_profile_read(ms, n, 1 if reset else 0))
+    return {STAGE_NAMES[i]: (ms[i], n[i]) for i in range(N_STAGES)}
+
+
+def launch_count() -> int:
+    return int(load().shb_launch_count())
+
+
+def _ptr(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+class SweepResult:
+    """Owner of one ``shb_result``.  Arrays are numpy views of backend-owned pinned memory and
+    stay valid while this object is alive."""
+
+    def __init__(self, handle, n_sweep: int, keepalive=None):
+        self._h = handle
+        self.n_sweep = n_sweep
+        self._keep = keepalive
+
+    def array(self, which: int, sweep: int = 0) -> np.ndarray:
+        shape = (C.c_int64 * 4)()
+        ndim, dt = C.c_int32(), C.c_int32()
+        ptr = load().shb_result_array(self._h, which, sweep, shape, C.byref(ndim), C.byref(dt))
+        if not ptr:
+            raise BackendError(load().shb_last_error().decode())
+        shp = tuple(int(shape[i]) for i in range(ndim.value))
+        dtype = np.dtype(_DTYPES[dt.value])
+        n = int(np.prod(shp)) if shp else 1
+        if n == 0:
+            return np.zeros(shp, dtype=dtype)
+        buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+        buf._shb_owner = self            # arr.base -> buf -> self keeps the pinned memory alive
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shp)
+        arr.flags.writeable = False
+        return arr
+
+    def fetch(self, mask: int) -> None:
+        check(load().shb_result_fetch(self._h, mask))
+
+    def totals(self):
+        v = [C.c_int64() for _ in range(4)]
+        check(load().shb_result_totals(self._h, *[C.byref(x) for x in v]))
+        return {"planes": v[0].value, "segments": v[1].value, "contours": v[2].value, "points": v[3].value}
+
+    def close(self):
+        if self._h:
+            load().shb_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _pack(meshes, sweeps):
+    """meshes: list of (vertices (V,3) f64, faces (T,3) i64); sweeps: list of
+    (mesh_index, z_orig, heights, interp_num)."""
+    verts = np.ascontiguousarray(np.concatenate([np.asarray(m[0], dtype=np.float64).reshape(-1, 3) for m in meshes]))
+    faces = np.ascontiguousarray(np.concatenate([np.asarray(m[1], dtype=np.int64).reshape(-1, 3) for m in meshes]))
+    vert_off = np.zeros(len(meshes) + 1, dtype=np.int64)
+    face_off = np.zeros(len(meshes) + 1, dtype=np.int64)
+    vert_off[1:] = np.cumsum([len(m[0]) for m in meshes])
+    face_off[1:] = np.cumsum([len(m[1]) for m in meshes])
+    sweep_mesh = np.array([s[0] for s in sweeps], dtype=np.int32)
+    z_orig = np.array([s[1] for s in sweeps], dtype=np.float64)
+    hs = [np.asarray(s[2], dtype=np.float64).reshape(-1) for s in sweeps]
+    heights = np.ascontiguousarray(np.concatenate(hs)) if hs else np.zeros(0)
+    height_off = np.zeros(len(sweeps) + 1, dtype=np.int64)
+    height_off[1:] = np.cumsum([len(h) for h in hs])
+    interp = np.array([s[3] for s in sweeps], dtype=np.int32)
+    return verts, vert_off, faces, face_off, sweep_mesh, z_orig, heights, height_off, interp
+
+
+class SweepBatch:
+    """HBM-resident meshes + sweeps (``shb_batch_create``); ``run`` enqueues the hot path."""
+
+    def __init__(self, meshes, sweeps, packed=None):
+        init(_inited if _inited is not None else 0)
+        a = packed if packed is not None else _pack(meshes, sweeps)
+        self.n_sweep = len(a[4])
+        h = C.c_void_p()
+        check(load().shb_batch_create(len(a[1]) - 1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), self.n_sweep,
+                                      _ptr(a[4]), _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), C.byref(h)))
+        self._h = h
+
+    def run(self, outputs_mask: int, n_angles: int = 0) -> SweepResult:
+        r = C.c_void_p()
+        check(load().shb_batch_run(self._h, outputs_mask, n_angles, C.byref(r)))
+        return SweepResult(r, self.n_sweep, keepalive=self)
+
+    def close(self):
+        if self._h:
+            load().shb_batch_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sweep_batch(meshes, sweeps, outputs_mask: int, n_angles: int = 0, packed=None) -> SweepResult:
+    """One-call host-to-host form (``shb_sweep_batch``)."""
+    init(_inited if _inited is not None else 0)
+    a = packed if packed is not None else _pack(meshes, sweeps)
+    r = C.c_void_p()
+    check(load().shb_sweep_batch(len(a[1]) - 1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), len(a[4]), _ptr(a[4]),
+                                 _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), outputs_mask, n_angles, C.byref(r)))
+    return SweepResult(r, len(a[4]))

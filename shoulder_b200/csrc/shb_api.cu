@@ -1,0 +1,585 @@
+// Host side of the C ABI declared in include/shoulder_b200.h: device bring-up, batch upload,
+// the launch sequence of the hot path, lazy device->host fetch of results.
+// Replaces the host loop of reference src/shoulder/humerus/slice.py:21-147 (one Python call into
+// trimesh + per-plane Python loops) with one enqueue of K1..K4 per batch.
+#include "shb_common.cuh"
+#include "../../include/shoulder_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <type_traits>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(SHB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct PinnedBuf { void* p; size_t size; bool used; };
+
+struct Ctx {
+    std::mutex mu;
+    bool inited = false;
+    int device = 0, n_sm = 148;
+    size_t smem_optin = 0;
+    cudaStream_t own = nullptr, stream = nullptr;
+    int64_t launches = 0;
+    bool profile = false;
+    double stage_ms[SHB_N_STAGES] = {};
+    int64_t stage_launches[SHB_N_STAGES] = {};
+    struct Pending { cudaEvent_t a, b; int stage; int n; };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> ev_free;
+    std::vector<PinnedBuf> pinned;
+    uint32_t* h_totals = nullptr;          // pinned readback slot
+    unsigned long long* h_totals64 = nullptr;
+} g;
+
+void* pinned_get(size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    PinnedBuf* best = nullptr;
+    for (auto& b : g.pinned)
+        if (!b.used && b.size >= bytes && (!best || b.size < best->size)) best = &b;
+    if (best && best->size <= 2 * bytes + (1 << 20)) { best->used = true; return best->p; }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    g.pinned.push_back({p, bytes, true});
+    return p;
+}
+void pinned_put(void* p) {
+    for (auto& b : g.pinned) if (b.p == p) { b.used = false; return; }
+}
+
+template <class T> cudaError_t dalloc(T** p, size_t n, cudaStream_t st) {
+    return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T), st);
+}
+template <class T> void dfree(T*& p, cudaStream_t st) { if (p) { cudaFreeAsync((void*)p, st); p = nullptr; } }
+
+struct StageTimer {
+    int stage; cudaEvent_t a = nullptr, b = nullptr; bool on;
+    explicit StageTimer(int s) : stage(s), on(g.profile) {
+        if (!on) return;
+        auto get = [] { cudaEvent_t e; if (!g.ev_free.empty()) { e = g.ev_free.back(); g.ev_free.pop_back(); } else cudaEventCreate(&e); return e; };
+        a = get(); b = get();
+        cudaEventRecord(a, g.stream);
+    }
+    void stop(int n_launch) {
+        g.launches += n_launch;
+        if (!on) return;
+        cudaEventRecord(b, g.stream);
+        g.pending.push_back({a, b, stage, n_launch});
+    }
+};
+
+}  // namespace
+
+struct shb_batch {
+    int32_t n_mesh = 0, n_sweep = 0;
+    int64_t n_vert = 0, n_face = 0;
+    uint32_t G = 0, n_item = 0, max_interp = 0;
+    uint64_t prof_total = 0;
+    std::vector<ShbSweep> sweeps;          // host copy
+    double4* vert = nullptr; double* vz = nullptr; int4* face = nullptr;
+    ShbSweep* d_sweep = nullptr; uint32_t* d_item_off = nullptr;
+    double* h_sorted = nullptr; double* h_orig = nullptr;
+    uint32_t *plane_out = nullptr, *plane_in = nullptr, *plane_sweep = nullptr;
+};
+
+struct shb_result {
+    const shb_batch* batch = nullptr;
+    std::vector<ShbSweep> sweeps;
+    uint32_t G = 0, mask = 0, n_angles = 0;
+    uint64_t prof_total = 0, rad_total = 0;
+    uint32_t W = 0;                         // capacity of the per-segment arrays
+    ShbDev d = {};                          // device pointers owned by the result
+    uint32_t* d_ct_off = nullptr; uint32_t* d_pt_off = nullptr;
+    double* d_pts_c = nullptr; int64_t* d_ctpt_c = nullptr; double* d_ctarea_c = nullptr;
+    // host (pinned) copies, filled lazily
+    bool have_plane = false, have_seg = false, have_cont = false;
+    uint32_t S = 0, n_cont = 0, n_pts = 0;
+    int32_t *h_nseg = nullptr, *h_nent = nullptr, *h_sel = nullptr, *h_face_index = nullptr;
+    uint32_t *h_status = nullptr, *h_seg_off = nullptr, *h_ct_off = nullptr, *h_pt_off = nullptr;
+    double *h_bounds = nullptr, *h_centroid = nullptr, *h_area1 = nullptr, *h_segments = nullptr;
+    double *h_pts = nullptr, *h_ctarea = nullptr; int64_t* h_ctpt = nullptr;
+    double* h_prof[6] = {}; double* h_radial = nullptr;
+    std::vector<std::vector<int64_t>> rel;  // per-sweep relative offset arrays handed out
+};
+
+extern "C" {
+
+SHB_API const char* shb_last_error(void) { return g_err.c_str(); }
+SHB_API int shb_abi_version(void) { return SHB_ABI_VERSION; }
+SHB_API int64_t shb_launch_count(void) { return g.launches; }
+
+SHB_API int shb_init(int device) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.inited) {
+        if (device != g.device) return fail(SHB_E_STATE, "already initialised on device %d", g.device);
+        return SHB_OK;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(SHB_E_CUDA, "no CUDA device (%s); this backend has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(SHB_E_INVALID, "device %d out of range [0,%d)", device, n);
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(SHB_E_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    g.device = device;
+    g.n_sm = prop.multiProcessorCount;
+    g.smem_optin = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
+    g.stream = g.own;
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CK(cudaMallocHost(&g.h_totals, 8 * sizeof(uint32_t)));
+    CK(cudaMallocHost(&g.h_totals64, 2 * sizeof(unsigned long long)));
+    g.inited = true;
+    return SHB_OK;
+}
+
+SHB_API int shb_set_stream(void* cuda_stream) {
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own;
+    return SHB_OK;
+}
+
+SHB_API int shb_profile_enable(int on) { g.profile = on != 0; return SHB_OK; }
+
+SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launches[SHB_N_STAGES], int reset) {
+    for (auto& p : g.pending) {
+        CK(cudaEventSynchronize(p.b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, p.a, p.b));
+        g.stage_ms[p.stage] += ms;
+        g.stage_launches[p.stage] += p.n;
+        g.ev_free.push_back(p.a); g.ev_free.push_back(p.b);
+    }
+    g.pending.clear();
+    for (int i = 0; i < SHB_N_STAGES; ++i) {
+        if (stage_ms) stage_ms[i] = g.stage_ms[i];
+        if (stage_launches) stage_launches[i] = g.stage_launches[i];
+        if (reset) { g.stage_ms[i] = 0; g.stage_launches[i] = 0; }
+    }
+    return SHB_OK;
+}
+
+SHB_API int shb_batch_free(shb_batch* b) {
+    if (!b) return SHB_OK;
+    cudaStream_t st = g.stream;
+    dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
+    dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st);
+    delete b;
+    return SHB_OK;
+}
+
+SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
+                     const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
+                     const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_batch** out) {
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (!out) return fail(SHB_E_INVALID, "out is null");
+    *out = nullptr;
+    if (n_mesh <= 0 || n_sweep <= 0 || !verts || !vert_off || !faces || !face_off || !sweep_mesh || !z_orig || !heights ||
+        !height_off || !interp_num)
+        return fail(SHB_E_INVALID, "null or empty input");
+    if (vert_off[0] != 0 || face_off[0] != 0 || height_off[0] != 0) return fail(SHB_E_INVALID, "offset arrays must start at 0");
+    for (int m = 0; m < n_mesh; ++m)
+        if (vert_off[m + 1] < vert_off[m] || face_off[m + 1] < face_off[m]) return fail(SHB_E_INVALID, "offsets of mesh %d decrease", m);
+    const int64_t nv = vert_off[n_mesh], nf = face_off[n_mesh], G64 = height_off[n_sweep];
+    if (nv >= (int64_t)1 << 31 || nf >= (int64_t)1 << 30) return fail(SHB_E_CAPACITY, "too many vertices/faces in one batch");
+    if (G64 <= 0 || G64 >= (int64_t)1 << 31) return fail(SHB_E_CAPACITY, "plane count %lld out of range", (long long)G64);
+
+    std::unique_ptr<shb_batch> b(new shb_batch);
+    b->n_mesh = n_mesh; b->n_sweep = n_sweep; b->n_vert = nv; b->n_face = nf; b->G = (uint32_t)G64;
+    b->sweeps.resize(n_sweep);
+    std::vector<uint32_t> item_off(n_sweep + 1, 0);
+    std::vector<double> hs(G64), ho(heights, heights + G64);
+    std::vector<uint32_t> pout(G64), pin(G64), psw(G64);
+    uint64_t prof = 0, items = 0;
+    std::vector<uint32_t> idx;
+    for (int s = 0; s < n_sweep; ++s) {
+        const int m = sweep_mesh[s];
+        const int64_t p0 = height_off[s], P = height_off[s + 1] - p0;
+        if (m < 0 || m >= n_mesh) return fail(SHB_E_INVALID, "sweep %d names mesh %d", s, m);
+        if (P < 0) return fail(SHB_E_INVALID, "height offsets of sweep %d decrease", s);
+        if (interp_num[s] < 2) return fail(SHB_E_INVALID, "interp_num of sweep %d must be >= 2", s);
+        ShbSweep& sw = b->sweeps[s];
+        sw.z_orig = z_orig[s]; sw.prof_off = prof; sw.rad_off = 0;
+        sw.plane_off = (uint32_t)p0; sw.n_plane = (uint32_t)P;
+        sw.face_off = (uint32_t)face_off[m]; sw.n_face = (uint32_t)(face_off[m + 1] - face_off[m]);
+        sw.item_off = (uint32_t)items; sw.interp_num = (uint32_t)interp_num[s]; sw.mesh = (uint32_t)m; sw.pad = 0;
+        item_off[s] = (uint32_t)items;
+        items += sw.n_face;
+        prof += (uint64_t)P * 2 * (uint64_t)interp_num[s];
+        b->max_interp = std::max<uint32_t>(b->max_interp, (uint32_t)interp_num[s]);
+        // planes ascending in height for the range search; linspace inputs are already monotone
+        const double* h = heights + p0;
+        bool asc = true, desc = true;
+        for (int64_t i = 1; i < P; ++i) { asc &= h[i] >= h[i - 1]; desc &= h[i] <= h[i - 1]; }
+        idx.resize(P);
+        if (asc) std::iota(idx.begin(), idx.end(), 0u);
+        else if (desc) for (int64_t i = 0; i < P; ++i) idx[i] = (uint32_t)(P - 1 - i);
+        else {
+            std::iota(idx.begin(), idx.end(), 0u);
+            std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t c) { return h[a] < h[c]; });
+        }
+        for (int64_t i = 0; i < P; ++i) {
+            if (!(h[idx[i]] == h[idx[i]])) return fail(SHB_E_INVALID, "NaN height in sweep %d", s);
+            hs[p0 + i] = h[idx[i]];
+            pout[p0 + i] = (uint32_t)(p0 + idx[i]);
+            pin[p0 + idx[i]] = (uint32_t)(p0 + i);
+            psw[p0 + i] = (uint32_t)s;
+        }
+    }
+    if (items >= (uint64_t)1 << 32) return fail(SHB_E_CAPACITY, "sum of faces over sweeps = %llu needs a split", (unsigned long long)items);
+    item_off[n_sweep] = (uint32_t)items;
+    b->n_item = (uint32_t)items; b->prof_total = prof;
+
+    cudaStream_t st = g.stream;
+    double* raw_v = nullptr; int64_t* raw_f = nullptr; int64_t *d_voff = nullptr, *d_foff = nullptr; uint32_t* d_bad = nullptr;
+    CK(dalloc(&raw_v, 3 * (size_t)nv, st)); CK(dalloc(&raw_f, 3 * (size_t)nf, st));
+    CK(dalloc(&d_voff, n_mesh + 1, st)); CK(dalloc(&d_foff, n_mesh + 1, st)); CK(dalloc(&d_bad, 1, st));
+    CK(dalloc(&b->vert, nv, st)); CK(dalloc(&b->vz, nv, st)); CK(dalloc(&b->face, nf, st));
+    CK(dalloc(&b->d_sweep, n_sweep, st)); CK(dalloc(&b->d_item_off, n_sweep + 1, st));
+    CK(dalloc(&b->h_sorted, G64, st)); CK(dalloc(&b->h_orig, G64, st));
+    CK(dalloc(&b->plane_out, G64, st)); CK(dalloc(&b->plane_in, G64, st)); CK(dalloc(&b->plane_sweep, G64, st));
+    CK(cudaMemcpyAsync(raw_v, verts, 3 * (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(raw_f, faces, 3 * (size_t)nf * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_voff, vert_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_foff, face_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), st));
+    CK(cudaMemcpyAsync(b->d_sweep, b->sweeps.data(), n_sweep * sizeof(ShbSweep), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->d_item_off, item_off.data(), (n_sweep + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->h_sorted, hs.data(), G64 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->h_orig, ho.data(), G64 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->plane_out, pout.data(), G64 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->plane_in, pin.data(), G64 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b->plane_sweep, psw.data(), G64 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, d_bad, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(g.h_totals, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st); dfree(d_bad, st);
+    CK(cudaStreamSynchronize(st));          // host staging vectors go out of scope below
+    if (g.h_totals[0]) { shb_batch_free(b.release()); return fail(SHB_E_INVALID, "face index out of range for its mesh"); }
+    *out = b.release();
+    return SHB_OK;
+}
+
+SHB_API int shb_result_free(shb_result* r) {
+    if (!r) return SHB_OK;
+    cudaStream_t st = g.stream;
+    ShbDev& d = r->d;
+    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.dec, st); dfree(d.sort_off, st);
+    dfree(d.sort_cur, st); dfree(d.cand_off, st); dfree(d.cnt, st); dfree(d.totals, st); dfree(d.totals64, st);
+    dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
+    dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
+    dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
+    dfree(d.ct_start, st); dfree(d.ct_len, st); dfree(d.ct_area, st);
+    for (int a = 0; a < 6; ++a) dfree(d.prof[a], st);
+    dfree(d.radial, st); dfree(d.scratch, st);
+    dfree(r->d_ct_off, st); dfree(r->d_pt_off, st); dfree(r->d_pts_c, st); dfree(r->d_ctpt_c, st); dfree(r->d_ctarea_c, st);
+    void* hp[] = {r->h_nseg, r->h_nent, r->h_sel, r->h_face_index, r->h_status, r->h_seg_off, r->h_ct_off, r->h_pt_off,
+                  r->h_bounds, r->h_centroid, r->h_area1, r->h_segments, r->h_pts, r->h_ctarea, r->h_ctpt, r->h_radial,
+                  r->h_prof[0], r->h_prof[1], r->h_prof[2], r->h_prof[3], r->h_prof[4], r->h_prof[5]};
+    for (void* p : hp) if (p) pinned_put(p);
+    delete r;
+    return SHB_OK;
+}
+
+SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles, shb_result** out) {
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (!b || !out) return fail(SHB_E_INVALID, "null batch/out");
+    *out = nullptr;
+    outputs_mask |= SHB_OUT_PLANE;
+    if ((outputs_mask & SHB_OUT_RADIAL) && n_angles < 1) return fail(SHB_E_INVALID, "n_angles must be >= 1 for the radial image");
+    if (!(outputs_mask & SHB_OUT_RADIAL)) n_angles = 0;
+    cudaStream_t st = g.stream;
+    const uint32_t G = b->G;
+    std::unique_ptr<shb_result> r(new shb_result);
+    r->batch = b; r->sweeps = b->sweeps; r->G = G; r->mask = outputs_mask; r->n_angles = (uint32_t)n_angles;
+    r->prof_total = b->prof_total; r->rel.resize((size_t)b->n_sweep * 3);
+    uint64_t rad = 0;
+    for (auto& sw : r->sweeps) { sw.rad_off = rad; rad += (uint64_t)sw.n_plane * (uint64_t)n_angles; }
+    r->rad_total = rad;
+    ShbDev& d = r->d;
+    d.vert = b->vert; d.vz = b->vz; d.face = b->face; d.item_off = b->d_item_off;
+    d.h_sorted = b->h_sorted; d.h_orig = b->h_orig; d.plane_out = b->plane_out; d.plane_in = b->plane_in; d.plane_sweep = b->plane_sweep;
+    d.n_sweep = (uint32_t)b->n_sweep; d.n_plane = G; d.n_item = b->n_item;
+    d.n_angles = (uint32_t)n_angles; d.outputs_mask = outputs_mask;
+    // sweep descriptors carry the radial offsets of this run
+    ShbSweep* d_sw = nullptr;
+    CK(dalloc(&d_sw, b->n_sweep, st));
+    CK(cudaMemcpyAsync(d_sw, r->sweeps.data(), b->n_sweep * sizeof(ShbSweep), cudaMemcpyHostToDevice, st));
+    d.sweep = d_sw;
+
+    CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st));
+    CK(dalloc(&d.inc, G + 1, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.sort_off, G + 1, st));
+    CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cand_off, G + 1, st)); CK(dalloc(&d.cnt, G, st));
+    CK(dalloc(&d.totals, 8, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
+    CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
+    CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
+    CK(dalloc(&d.o_sel, 2 * (size_t)G, st));
+    CK(cudaMemsetAsync(d.inc, 0, (G + 1) * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, (G + 1) * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.cnt, 0, G * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d.totals, 0, 8 * sizeof(uint32_t), st));
+
+    { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
+    { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
+    CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(g.h_totals64, d.totals64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));          // the one mid-pipeline sync: sizes of everything downstream
+    const uint32_t M = g.h_totals[SHB_T_M], W = g.h_totals[SHB_T_W], maxcand = g.h_totals[SHB_T_MAXCAND];
+    if (g.h_totals64[0] >= (1ull << 31)) {
+        shb_result* rr = r.release(); cudaFreeAsync(d_sw, st); rr->d.sweep = nullptr; shb_result_free(rr);
+        return fail(SHB_E_CAPACITY, "%llu candidate segments in one batch; split it", g.h_totals64[0]);
+    }
+    r->W = W;
+    CK(dalloc(&d.rec, M, st)); CK(dalloc(&d.hits, W, st));
+    CK(dalloc(&d.face_index, W, st)); CK(dalloc(&d.segments, 4 * (size_t)W, st)); CK(dalloc(&d.pts, 4 * (size_t)W + 4, st));
+    CK(dalloc(&d.ct_start, W, st)); CK(dalloc(&d.ct_len, W, st)); CK(dalloc(&d.ct_area, W, st));
+    const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
+                              SHB_OUT_ITR_CENTERED_START};
+    bool any_prof = false;
+    for (int a = 0; a < 6; ++a)
+        if (outputs_mask & pbit[a]) { CK(dalloc(&d.prof[a], r->prof_total, st)); any_prof = true; }
+    if (outputs_mask & SHB_OUT_RADIAL) { CK(dalloc(&d.radial, r->rad_total, st)); any_prof = true; }
+
+    // shared-memory capacities (leave headroom for static shared memory)
+    const size_t budget = (g.smem_optin > 8192 ? g.smem_optin - 4096 : 40960);
+    uint32_t cap = 1;
+    for (uint32_t step = 1u << 20; step; step >>= 1)
+        if (shb_stitch_ws_bytes(cap + step) <= budget) cap += step;
+    d.stitch_cap = cap;
+    uint32_t pcap = 2;
+    for (uint32_t step = 1u << 20; step; step >>= 1)
+        if (shb_resample_ws_bytes(pcap + step, b->max_interp, (uint32_t)n_angles) <= budget) pcap += step;
+    d.resample_cap = pcap;
+    if (maxcand > cap || 2 * (size_t)maxcand + 2 > pcap) {
+        size_t s1 = shb_stitch_ws_bytes(maxcand), s2 = shb_resample_ws_bytes(2 * maxcand + 2, b->max_interp, (uint32_t)n_angles);
+        d.scratch_stride = (std::max(s1, s2) + 255) & ~(size_t)255;
+        CK(dalloc(&d.scratch, d.scratch_stride * (size_t)g.n_sm, st));
+    }
+
+    { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
+    { StageTimer t(3); t.stop(shb_launch_intersect(d, M, st)); }
+    { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
+    { StageTimer t(5); t.stop(shb_launch_stitch(d, maxcand, g.n_sm, st)); }
+    if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, b->max_interp, g.n_sm, st)); }
+    CK(cudaGetLastError());
+    // stage scratch is dead once the kernels above are enqueued (stream ordered)
+    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.dec, st); dfree(d.sort_off, st);
+    dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st); dfree(d.cand_off, st);
+    dfree(d.cnt, st); dfree(d.scratch, st);
+    cudaFreeAsync(d_sw, st); d.sweep = nullptr;
+    *out = r.release();
+    return SHB_OK;
+}
+
+static int fetch_plane(shb_result* r) {
+    if (r->have_plane) return SHB_OK;
+    cudaStream_t st = g.stream;
+    const size_t G = r->G;
+    auto grab = [&](auto** hp, const void* dp, size_t bytes) -> int {
+        *hp = reinterpret_cast<std::remove_pointer_t<decltype(hp)>>(pinned_get(bytes));
+        if (!*hp) return fail(SHB_E_NOMEM, "pinned host allocation of %zu bytes failed", bytes);
+        CK(cudaMemcpyAsync(*hp, dp, bytes, cudaMemcpyDeviceToHost, st));
+        return SHB_OK;
+    };
+    int rc;
+    if ((rc = grab(&r->h_nseg, r->d.o_nseg, G * 4))) return rc;
+    if ((rc = grab(&r->h_nent, r->d.o_nent, G * 4))) return rc;
+    if ((rc = grab(&r->h_status, r->d.o_status, G * 4))) return rc;
+    if ((rc = grab(&r->h_sel, r->d.o_sel, G * 8))) return rc;
+    if ((rc = grab(&r->h_bounds, r->d.o_bounds, G * 32))) return rc;
+    if ((rc = grab(&r->h_centroid, r->d.o_centroid, G * 16))) return rc;
+    if ((rc = grab(&r->h_area1, r->d.o_area1, G * 8))) return rc;
+    if ((rc = grab(&r->h_seg_off, r->d.seg_off, (G + 1) * 4))) return rc;
+    CK(cudaStreamSynchronize(st));
+    r->S = r->h_seg_off[G];
+    r->have_plane = true;
+    return SHB_OK;
+}
+
+SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
+    if (!r) return fail(SHB_E_INVALID, "null result");
+    cudaStream_t st = g.stream;
+    int rc = fetch_plane(r);
+    if (rc) return rc;
+    bool sync = false;
+    if ((mask & SHB_OUT_SEGMENTS) && !r->have_seg) {
+        const size_t S = r->S;
+        r->h_face_index = (int32_t*)pinned_get(S * 4); r->h_segments = (double*)pinned_get(S * 32);
+        if (!r->h_face_index || !r->h_segments) return fail(SHB_E_NOMEM, "pinned host allocation failed");
+        CK(cudaMemcpyAsync(r->h_face_index, r->d.face_index, S * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->h_segments, r->d.segments, S * 32, cudaMemcpyDeviceToHost, st));
+        r->have_seg = true; sync = true;
+    }
+    if ((mask & SHB_OUT_CONTOURS) && !r->have_cont) {
+        const size_t G = r->G;
+        ShbDev d = r->d;
+        ShbSweep* d_sw = nullptr;                       // compaction does not read sweeps, but keep ShbDev whole
+        (void)d_sw;
+        CK(dalloc(&r->d_ct_off, G + 1, st)); CK(dalloc(&r->d_pt_off, G + 1, st));
+        g.launches += shb_launch_scan_contours(d, r->d_ct_off, r->d_pt_off, st);
+        CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        r->n_cont = g.h_totals[SHB_T_NCONT]; r->n_pts = g.h_totals[SHB_T_NPTS];
+        CK(dalloc(&r->d_pts_c, 2 * (size_t)r->n_pts, st)); CK(dalloc(&r->d_ctpt_c, (size_t)r->n_cont + 1, st));
+        CK(dalloc(&r->d_ctarea_c, r->n_cont, st));
+        g.launches += shb_launch_compact(d, r->d_ct_off, r->d_pt_off, r->d_pts_c, r->d_ctpt_c, r->d_ctarea_c, st);
+        CK(cudaGetLastError());
+        r->h_ct_off = (uint32_t*)pinned_get((G + 1) * 4); r->h_pt_off = (uint32_t*)pinned_get((G + 1) * 4);
+        r->h_pts = (double*)pinned_get((size_t)r->n_pts * 16); r->h_ctpt = (int64_t*)pinned_get(((size_t)r->n_cont + 1) * 8);
+        r->h_ctarea = (double*)pinned_get((size_t)r->n_cont * 8);
+        if (!r->h_ct_off || !r->h_pt_off || !r->h_pts || !r->h_ctpt || !r->h_ctarea) return fail(SHB_E_NOMEM, "pinned host allocation failed");
+        CK(cudaMemcpyAsync(r->h_ct_off, r->d_ct_off, (G + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->h_pt_off, r->d_pt_off, (G + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->h_pts, r->d_pts_c, (size_t)r->n_pts * 16, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->h_ctpt, r->d_ctpt_c, ((size_t)r->n_cont + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->h_ctarea, r->d_ctarea_c, (size_t)r->n_cont * 8, cudaMemcpyDeviceToHost, st));
+        r->have_cont = true; sync = true;
+    }
+    const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
+                              SHB_OUT_ITR_CENTERED_START};
+    for (int a = 0; a < 6; ++a)
+        if ((mask & pbit[a]) && !r->h_prof[a]) {
+            if (!r->d.prof[a]) return fail(SHB_E_STATE, "profile array %d was not in the outputs_mask of the run", a);
+            r->h_prof[a] = (double*)pinned_get(r->prof_total * 8);
+            if (!r->h_prof[a]) return fail(SHB_E_NOMEM, "pinned host allocation failed");
+            CK(cudaMemcpyAsync(r->h_prof[a], r->d.prof[a], r->prof_total * 8, cudaMemcpyDeviceToHost, st));
+            sync = true;
+        }
+    if ((mask & SHB_OUT_RADIAL) && !r->h_radial) {
+        if (!r->d.radial) return fail(SHB_E_STATE, "radial image was not in the outputs_mask of the run");
+        r->h_radial = (double*)pinned_get(r->rad_total * 8);
+        if (!r->h_radial) return fail(SHB_E_NOMEM, "pinned host allocation failed");
+        CK(cudaMemcpyAsync(r->h_radial, r->d.radial, r->rad_total * 8, cudaMemcpyDeviceToHost, st));
+        sync = true;
+    }
+    if (sync) CK(cudaStreamSynchronize(st));
+    return SHB_OK;
+}
+
+SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n_seg, int64_t* n_contour, int64_t* n_point) {
+    shb_result* r = const_cast<shb_result*>(r_);
+    if (!r) return fail(SHB_E_INVALID, "null result");
+    int rc = fetch_plane(r);
+    if (rc) return rc;
+    if (n_plane) *n_plane = r->G;
+    if (n_seg) *n_seg = r->S;
+    if (n_contour || n_point) {
+        int64_t c = 0, p = 0;
+        if (r->have_cont) { c = r->n_cont; p = r->n_pts; }
+        else for (uint32_t i = 0; i < r->G; ++i) c += r->h_nent[i];
+        if (n_contour) *n_contour = c;
+        if (n_point) *n_point = r->have_cont ? p : -1;
+    }
+    return SHB_OK;
+}
+
+SHB_API const void* shb_result_array(shb_result* r, int32_t which, int32_t sweep, int64_t shape[4], int32_t* ndim, int32_t* dtype) {
+    if (!r || !shape || !ndim || !dtype) { fail(SHB_E_INVALID, "null argument"); return nullptr; }
+    if (sweep < 0 || sweep >= (int32_t)r->sweeps.size()) { fail(SHB_E_INVALID, "sweep %d out of range", sweep); return nullptr; }
+    uint32_t need = SHB_OUT_PLANE;
+    switch (which) {
+        case SHB_ARR_FACE_INDEX: case SHB_ARR_SEGMENTS: need = SHB_OUT_SEGMENTS; break;
+        case SHB_ARR_CONTOUR_OFF: case SHB_ARR_CONTOUR_PT_OFF: case SHB_ARR_CONTOUR_AREA: case SHB_ARR_POINTS: need = SHB_OUT_CONTOURS; break;
+        case SHB_ARR_IXY: need = SHB_OUT_IXY; break;
+        case SHB_ARR_IXY_CENTERED: need = SHB_OUT_IXY_CENTERED; break;
+        case SHB_ARR_ITR: need = SHB_OUT_ITR; break;
+        case SHB_ARR_ITR_START: need = SHB_OUT_ITR_START; break;
+        case SHB_ARR_ITR_CENTERED: need = SHB_OUT_ITR_CENTERED; break;
+        case SHB_ARR_ITR_CENTERED_START: need = SHB_OUT_ITR_CENTERED_START; break;
+        case SHB_ARR_RADIAL: need = SHB_OUT_RADIAL; break;
+        default: break;
+    }
+    if (which < 0 || which >= SHB_ARR_COUNT) { fail(SHB_E_INVALID, "unknown array id %d", which); return nullptr; }
+    if (shb_result_fetch(r, need) != SHB_OK) return nullptr;
+    const ShbSweep& sw = r->sweeps[sweep];
+    const size_t p0 = sw.plane_off, P = sw.n_plane, N = sw.interp_num;
+    auto rel = [&](int slot, const uint32_t* src, size_t first, size_t count) -> const void* {
+        std::vector<int64_t>& v = r->rel[(size_t)sweep * 3 + slot];
+        v.resize(count);
+        for (size_t i = 0; i < count; ++i) v[i] = (int64_t)src[first + i] - (int64_t)src[first];
+        return v.data();
+    };
+    *ndim = 1; shape[0] = (int64_t)P; shape[1] = shape[2] = shape[3] = 0;
+    switch (which) {
+        case SHB_ARR_N_SEG: *dtype = SHB_DT_I32; return r->h_nseg + p0;
+        case SHB_ARR_N_ENT: *dtype = SHB_DT_I32; return r->h_nent + p0;
+        case SHB_ARR_STATUS: *dtype = SHB_DT_U32; return r->h_status + p0;
+        case SHB_ARR_AREA1: *dtype = SHB_DT_F64; return r->h_area1 + p0;
+        case SHB_ARR_SEL: *dtype = SHB_DT_I32; *ndim = 2; shape[1] = 2; return r->h_sel + 2 * p0;
+        case SHB_ARR_BOUNDS: *dtype = SHB_DT_F64; *ndim = 3; shape[1] = 2; shape[2] = 2; return r->h_bounds + 4 * p0;
+        case SHB_ARR_CENTROID: *dtype = SHB_DT_F64; *ndim = 2; shape[1] = 2; return r->h_centroid + 2 * p0;
+        case SHB_ARR_SEG_OFF: *dtype = SHB_DT_I64; shape[0] = (int64_t)P + 1; return rel(0, r->h_seg_off, p0, P + 1);
+        case SHB_ARR_FACE_INDEX: *dtype = SHB_DT_I32; shape[0] = (int64_t)r->h_seg_off[p0 + P] - r->h_seg_off[p0];
+            return r->h_face_index + r->h_seg_off[p0];
+        case SHB_ARR_SEGMENTS: *dtype = SHB_DT_F64; *ndim = 3; shape[0] = (int64_t)r->h_seg_off[p0 + P] - r->h_seg_off[p0];
+            shape[1] = 2; shape[2] = 2; return r->h_segments + 4 * (size_t)r->h_seg_off[p0];
+        case SHB_ARR_CONTOUR_OFF: *dtype = SHB_DT_I64; shape[0] = (int64_t)P + 1; return rel(1, r->h_ct_off, p0, P + 1);
+        case SHB_ARR_CONTOUR_AREA: *dtype = SHB_DT_F64; shape[0] = (int64_t)r->h_ct_off[p0 + P] - r->h_ct_off[p0];
+            return r->h_ctarea + r->h_ct_off[p0];
+        case SHB_ARR_CONTOUR_PT_OFF: {
+            *dtype = SHB_DT_I64;
+            const size_t c0 = r->h_ct_off[p0], c1 = r->h_ct_off[p0 + P];
+            std::vector<int64_t>& v = r->rel[(size_t)sweep * 3 + 2];
+            v.resize(c1 - c0 + 1);
+            const int64_t base = r->h_pt_off[p0];
+            for (size_t c = c0; c < c1; ++c) v[c - c0] = r->h_ctpt[c] - base;
+            v[c1 - c0] = (int64_t)r->h_pt_off[p0 + P] - base;
+            shape[0] = (int64_t)(c1 - c0 + 1);
+            return v.data();
+        }
+        case SHB_ARR_POINTS: *dtype = SHB_DT_F64; *ndim = 2; shape[0] = (int64_t)r->h_pt_off[p0 + P] - r->h_pt_off[p0]; shape[1] = 2;
+            return r->h_pts + 2 * (size_t)r->h_pt_off[p0];
+        case SHB_ARR_RADIAL: *dtype = SHB_DT_F64; *ndim = 2; shape[1] = r->n_angles; return r->h_radial + sw.rad_off;
+        default: {
+            const int a = which - SHB_ARR_IXY;
+            *dtype = SHB_DT_F64; *ndim = 3; shape[1] = 2; shape[2] = (int64_t)N;
+            return r->h_prof[a] + sw.prof_off;
+        }
+    }
+}
+
+SHB_API int shb_sweep_batch(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
+                    const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
+                    const double* heights, const int64_t* height_off, const int32_t* interp_num, uint32_t outputs_mask,
+                    int32_t n_angles, shb_result** out) {
+    shb_batch* b = nullptr;
+    int rc = shb_batch_create(n_mesh, verts, vert_off, faces, face_off, n_sweep, sweep_mesh, z_orig, heights, height_off, interp_num, &b);
+    if (rc) return rc;
+    rc = shb_batch_run(b, outputs_mask, n_angles, out);
+    if (rc) { shb_batch_free(b); return rc; }
+    rc = shb_result_fetch(*out, outputs_mask | SHB_OUT_PLANE);
+    (*out)->batch = nullptr;
+    shb_batch_free(b);                    // stream ordered: the result no longer reads the inputs
+    if (rc) { shb_result_free(*out); *out = nullptr; }
+    return rc;
+}
+
+}  // extern "C"

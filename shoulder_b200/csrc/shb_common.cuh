@@ -1,0 +1,132 @@
+// Shared declarations of the sm_100a slicing backend (host + device).
+// Path replaced: reference src/shoulder/humerus/slice.py:21-147 and the trimesh calls under it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SHB_TOL_MERGE 1e-8     // trimesh.constants.tol.merge  (sign classification band)
+
+// sweep descriptor, one per (mesh, height list) pair — device resident
+struct ShbSweep {
+    double   z_orig;      // plane origin z (slice.py:18)
+    uint64_t prof_off;    // offset in doubles of this sweep's (P,2,N) block in every profile array
+    uint64_t rad_off;     // offset in doubles of this sweep's (P,A) block in the radial image
+    uint32_t plane_off;   // first global plane index
+    uint32_t n_plane;
+    uint32_t face_off;    // first global face index of the sweep's mesh
+    uint32_t n_face;
+    uint32_t item_off;    // first (sweep, triangle) work item
+    uint32_t interp_num;  // N
+    uint32_t mesh;
+    uint32_t pad;
+};
+
+// per-plane record written by the stitch kernel (original plane order)
+struct ShbPlaneMeta {
+    double   bounds[4];   // minx, miny, maxx, maxy   (Path2D.bounds)
+    double   centroid[2]; // bounds midpoint           (Path2D.centroid, slice.py:38)
+    double   area1;       // slice.py:49-60
+    uint32_t n_seg;
+    uint32_t n_ent;       // len(Path2D.entities)
+    uint32_t status;      // SHB_ST_*
+    uint32_t sel_contour; // contour the outline is taken from (slice.py:70-76)
+    uint32_t sel_start;   // its first point, relative to the plane's point region
+    uint32_t sel_len;     // its point count including the closing duplicate
+    uint32_t n_pts;       // points written for the plane (closing duplicates included)
+    uint32_t pad;
+};
+
+struct ShbDev {
+    // ---- batch-static inputs
+    const double4*  vert;        // (x, y, z, 0) per global vertex
+    const double*   vz;          // z only (dense, for the bucket / intersect kernels)
+    const int4*     face;        // global vertex ids (a, b, c, 0) per global face
+    const ShbSweep* sweep;
+    const uint32_t* item_off;    // [n_sweep+1] prefix of faces per sweep
+    const double*   h_sorted;    // [G] heights ascending within each sweep
+    const double*   h_orig;      // [G] heights in caller order (indexed by original plane)
+    const uint32_t* plane_out;   // [G] sorted plane -> original global plane
+    const uint32_t* plane_in;    // [G] original global plane -> sorted plane
+    const uint32_t* plane_sweep; // [G] sweep of sorted plane
+    uint32_t n_sweep, n_plane /*G*/, n_item;
+    // ---- per-run scratch
+    uint32_t* item_lo;    // [n_item] first sorted plane of the triangle's range
+    uint32_t* item_span;  // [n_item]
+    uint32_t* inc;        // [G+1] #triangles whose range starts at plane
+    uint32_t* dec;        // [G+1] #triangles whose range ends before plane
+    uint32_t* sort_off;   // [G+1]
+    uint32_t* sort_cur;   // [G]
+    uint32_t* cand_off;   // [G+1] capacity offsets of the per-plane hit lists
+    uint32_t* cnt;        // [G]   exact hits per sorted plane
+    uint32_t* totals;     // [8]   M, W, maxcand, S, maxn, nbig, ...
+    uint4*    rec;        // [M]   bucketed triangles (face, lo, span, sweep)
+    uint32_t* hits;       // [W]   per-plane lists of global face ids
+    uint32_t* seg_off;    // [G+1] exact segment offsets, original plane order
+    uint32_t* big_list;   // [G]   planes too large for shared memory
+    // ---- outputs (device)
+    ShbPlaneMeta* meta;   // [G]  (kernel-internal AoS; the arrays below are what the host reads)
+    int32_t*  o_nseg;     // [G]
+    int32_t*  o_nent;     // [G]
+    uint32_t* o_status;   // [G]
+    double*   o_bounds;   // [G][4]
+    double*   o_centroid; // [G][2]
+    double*   o_area1;    // [G]
+    int32_t*  o_sel;      // [G][2]
+    unsigned long long* totals64;  // [2] 64-bit candidate total (overflow guard)
+    int32_t*  face_index; // [S]
+    double*   segments;   // [S][2][2]
+    double*   pts;        // [2S][2] capacity layout: plane p owns [2*seg_off[p], 2*seg_off[p+1])
+    uint32_t* ct_start;   // [S] capacity layout: plane p owns [seg_off[p], seg_off[p+1])
+    uint32_t* ct_len;     // [S]
+    double*   ct_area;    // [S]
+    double*   prof[6];    // ixy, ixy_centered, itr, itr_start, itr_centered, itr_centered_start
+    double*   radial;
+    unsigned char* scratch;      // global workspaces for oversized planes
+    size_t    scratch_stride;
+    uint32_t  n_angles;
+    uint32_t  outputs_mask;
+    uint32_t  stitch_cap;        // largest n handled in shared memory
+    uint32_t  resample_cap;      // largest point count handled in shared memory
+};
+
+enum { SHB_T_M = 0, SHB_T_W = 1, SHB_T_MAXCAND = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
+       SHB_T_NCONT = 6, SHB_T_NPTS = 7 };
+
+// bytes of workspace the stitch kernel needs for a plane with n segments
+__host__ __device__ inline uint32_t shb_pow2_ge(uint32_t x) {
+    uint32_t p = 1;
+    while (p < x) p <<= 1;
+    return p;
+}
+__host__ __device__ inline uint32_t shb_hash_size(uint32_t n) { return shb_pow2_ge(2 * n + n / 2 + 1); }
+__host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
+    size_t E = 2 * (size_t)n;
+    size_t c1 = 4 * (size_t)shb_pow2_ge(n) + 4 * (size_t)shb_hash_size(n);   // sort keys + hash table
+    size_t c2 = 12 * E;                                                       // jump pairs + heads
+    size_t c = c1 > c2 ? c1 : c2;
+    return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + 64;
+}
+__host__ __device__ inline size_t shb_resample_ws_bytes(uint32_t npts, uint32_t N, uint32_t A) {
+    return 24 * ((size_t)npts + 1) + 32 * (size_t)N + 12 * (size_t)shb_pow2_ge(N) + 8 * (size_t)A + 64;
+}
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+// launch wrappers (shb_kernels.cu); every one returns the number of kernels it enqueued
+int shb_launch_prep_mesh(const double* verts_in, const int64_t* faces_in, const int64_t* vert_off,
+                         const int64_t* face_off, int n_mesh, int64_t n_vert, int64_t n_face,
+                         double4* vert, double* vz, int4* face, uint32_t* bad, cudaStream_t st);
+int shb_launch_bucket(const ShbDev& d, cudaStream_t st);
+int shb_launch_scan_planes(const ShbDev& d, cudaStream_t st);
+int shb_launch_scatter(const ShbDev& d, cudaStream_t st);
+int shb_launch_intersect(const ShbDev& d, uint32_t M, cudaStream_t st);
+int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
+int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, int n_sm, cudaStream_t st);
+int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t maxN, int n_sm, cudaStream_t st);
+int shb_launch_compact(const ShbDev& d, const uint32_t* ct_off, const uint32_t* pt_off,
+                       double* pts_out, int64_t* ctpt_out, double* ctarea_out, cudaStream_t st);
+int shb_launch_scan_contours(const ShbDev& d, uint32_t* ct_off, uint32_t* pt_off, cudaStream_t st);
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,144 @@
+"""Per-plane view with the ``trimesh.path.Path2D`` attributes the reference reads.
+
+Consumers in the reference: ``slice.py:38,53-59,70-76`` (centroid, entities, polygons_closed,
+area, discrete), ``canal.py:46`` (centroid), ``epicondyle.py:36,43`` (polygons_closed[0]),
+``mesh.py:102`` (vertices), plus ``metadata['face_index']`` / ``['to_3D']`` which
+``section_multiplane`` attaches.  Everything is a lazy view into one ``SweepResult``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+try:  # real shapely polygons when the host has shapely (epicondyle.py needs GEOS operations)
+    from shapely.geometry import Polygon as _ShapelyPolygon
+except Exception:  # pragma: no cover - not installed in the build image
+    _ShapelyPolygon = None
+
+
+class _Polygon:
+    """Minimal stand-in when shapely is absent: the ring and the area the device computed."""
+
+    def __init__(self, ring: np.ndarray, area: float):
+        self.ring = ring
+        self.area = float(area)
+
+    @property
+    def exterior_coords(self) -> np.ndarray:
+        return self.ring
+
+
+class _Entity:
+    """Closed polyline entity (``trimesh.path.entities.Line``): only ``len(entities)`` and
+    ``closed`` / ``points`` are meaningful."""
+
+    closed = True
+
+    def __init__(self, points: np.ndarray):
+        self.points = points
+
+
+def _point_in_ring(p, ring) -> bool:
+    x, y = p
+    x0, y0, x1, y1 = ring[:-1, 0], ring[:-1, 1], ring[1:, 0], ring[1:, 1]
+    cond = (y0 > y) != (y1 > y)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        xint = x0 + (y - y0) * (x1 - x0) / (y1 - y0)
+    return bool((cond & (x < xint)).sum() % 2 == 1)
+
+
+class GpuPath2D:
+    def __init__(self, result: "_lib.SweepResult", sweep: int, plane: int, z: float):
+        self._res, self._k, self._i, self._z = result, sweep, plane, z
+
+    def _a(self, which):
+        return self._res.array(which, self._k)
+
+    # ---- per-plane scalars ------------------------------------------------------------------
+    @property
+    def status(self) -> int:
+        return int(self._a(_lib.ARR_STATUS)[self._i])
+
+    @property
+    def bounds(self) -> np.ndarray:
+        return np.array(self._a(_lib.ARR_BOUNDS)[self._i])
+
+    @property
+    def centroid(self) -> np.ndarray:
+        return np.array(self._a(_lib.ARR_CENTROID)[self._i])
+
+    # ---- contours ---------------------------------------------------------------------------
+    def _contour_range(self):
+        off = self._a(_lib.ARR_CONTOUR_OFF)
+        return int(off[self._i]), int(off[self._i + 1])
+
+    @property
+    def discrete(self):
+        c0, c1 = self._contour_range()
+        ptoff = self._a(_lib.ARR_CONTOUR_PT_OFF)
+        pts = self._a(_lib.ARR_POINTS)
+        return [np.array(pts[int(ptoff[c]):int(ptoff[c + 1])]) for c in range(c0, c1)]
+
+    @property
+    def entities(self):
+        n = int(self._a(_lib.ARR_N_ENT)[self._i])
+        lens = [len(d) for d in self.discrete] if n else []
+        out, first = [], 0
+        for m in lens:
+            idx = np.r_[np.arange(first, first + m - 1), first]
+            out.append(_Entity(idx))
+            first += m - 1
+        return out
+
+    @property
+    def vertices(self) -> np.ndarray:
+        d = self.discrete
+        return np.vstack([c[:-1] for c in d]) if d else np.zeros((0, 2))
+
+    @property
+    def polygons_closed(self):
+        c0, c1 = self._contour_range()
+        areas = self._a(_lib.ARR_CONTOUR_AREA)
+        out = []
+        for c, ring in zip(range(c0, c1), self.discrete):
+            if len(ring) < 4:
+                out.append(None)
+            elif _ShapelyPolygon is not None:
+                out.append(_ShapelyPolygon(ring))
+            else:
+                out.append(_Polygon(ring, areas[c]))
+        return out
+
+    @property
+    def area(self) -> float:
+        """``Path2D.area``: shells minus the holes directly inside them (``polygons_full``)."""
+        polys = [p for p in self.polygons_closed if p is not None]
+        if len(polys) == 1:
+            return float(polys[0].area)
+        rings = [np.asarray(p.exterior.coords) if _ShapelyPolygon is not None and isinstance(p, _ShapelyPolygon)
+                 else p.ring for p in polys]
+        depth = [sum(_point_in_ring(rings[i][0], rings[j]) for j in range(len(rings)) if j != i)
+                 for i in range(len(rings))]
+        total = 0.0
+        for i, p in enumerate(polys):
+            if depth[i] % 2:
+                continue
+            total += p.area
+            for j, q in enumerate(polys):
+                if depth[j] == depth[i] + 1 and _point_in_ring(rings[j][0], rings[i]):
+                    total -= q.area
+        return float(total)
+
+    # ---- what section_multiplane attaches ---------------------------------------------------
+    @property
+    def metadata(self):
+        off = self._a(_lib.ARR_SEG_OFF)
+        s0, s1 = int(off[self._i]), int(off[self._i + 1])
+        to_3d = np.eye(4)
+        to_3d[2, 3] = self._z
+        return {
+            "face_index": np.array(self._a(_lib.ARR_FACE_INDEX)[s0:s1], dtype=np.int64),
+            "segments": np.array(self._a(_lib.ARR_SEGMENTS)[s0:s1]),
+            "to_3D": to_3d,
+        }

@@ -1,0 +1,221 @@
+"""GPU slice provider — host-side mirror of reference ``src/shoulder/humerus/slice.py``.
+
+``GpuFullSlices`` / ``GpuProximalSlices`` / ``GpuDistalSlices`` take the constructor arguments
+of the reference's ``FullSlices`` (slice.py:209-224), ``ProximalSlices`` (:227-253) and
+``DistalSlices`` (:256-276) and expose the accessor set of ``Slices`` (:31-155) with the same
+names, argument meaning, windowing (:157-164) and quirks:
+
+  * ``itr(cutoff)`` hands back the *cartesian* ``_ixy`` window (slice.py:99-100),
+  * ``itr_start_even_theta(cutoff)`` hands back ``_itr_start`` (slice.py:121-122),
+  * ``_cutoff`` truncates with ``int()`` and can drop a row to force odd length.
+
+Everything numeric comes from one call into ``libshoulder_b200.so`` per object (or per batch of
+objects, see :func:`run_batch`); arrays are fetched from the device lazily, on first access, the
+way the reference memoises with ``cached_property``.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from functools import cached_property
+
+import numpy as np
+
+from . import _lib
+from .path2d import GpuPath2D
+
+_PROFILE_ARRAYS = {
+    "_ixy": _lib.ARR_IXY,
+    "_ixy_centered": _lib.ARR_IXY_CENTERED,
+    "_itr": _lib.ARR_ITR,
+    "_itr_start": _lib.ARR_ITR_START,
+    "_itr_centered": _lib.ARR_ITR_CENTERED,
+    "_itr_centered_start": _lib.ARR_ITR_CENTERED_START,
+}
+_RUN_MASK = _lib.OUT_PLANE | _lib.OUT_ALL_PROFILES
+
+
+class GpuSlices:
+    """Common part (reference ``Slices``, slice.py:9-207)."""
+
+    def __init__(self, obb, zslice_num: int, interp_num: int, return_odd: bool = False):
+        self._mesh_oriented_uobb = obb.mesh
+        self.obb = obb
+        self.return_odd = return_odd
+        self._zslice_num = zslice_num
+        self._interp_num = interp_num
+        self._z_orig = np.mean(self._zs)
+        self._z_incrs = self._zs - self._z_orig
+        self._attached = None            # (SweepResult, sweep index) when filled by run_batch
+
+    # ---- backend call -------------------------------------------------------------------
+    def _sweep_spec(self, mesh_index: int = 0):
+        return (mesh_index, float(self._z_orig), np.asarray(self._z_incrs, dtype=np.float64), int(self._interp_num))
+
+    def _mesh_arrays(self):
+        m = self.obb.mesh
+        return np.asarray(m.vertices, dtype=np.float64), np.asarray(m.faces, dtype=np.int64)
+
+    @cached_property
+    def _result(self):
+        if self._attached is not None:
+            return self._attached
+        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], _RUN_MASK)
+        return res, 0
+
+    def _arr(self, which: int) -> np.ndarray:
+        res, k = self._result
+        return res.array(which, k)
+
+    # ---- what slice.py caches -----------------------------------------------------------
+    @cached_property
+    def _slices(self):
+        res, k = self._result
+        status = self._arr(_lib.ARR_STATUS)
+        return [None if status[i] & _lib.ST_EMPTY else GpuPath2D(res, k, i, float(self._zs[i]))
+                for i in range(len(self._z_incrs))]
+
+    @cached_property
+    def _centroids(self):
+        self._require_sections()
+        return np.array(self._arr(_lib.ARR_CENTROID))
+
+    @cached_property
+    def _centroids_repeated(self):
+        return np.repeat(self._centroids.reshape(-1, 2, 1), self._interp_num, axis=2)
+
+    @cached_property
+    def _areas1(self):
+        self._require_sections()
+        area = np.array(self._arr(_lib.ARR_AREA1))
+        n_ent = self._arr(_lib.ARR_N_ENT)
+        # one entity: slice.py:59 asks Path2D.area; identical to the polygon's own area.
+        # several entities: slice.py:55-57 takes the largest closed polygon — what the device stored.
+        assert (n_ent >= 1).all()
+        return area
+
+    @cached_property
+    def _itr_start_even_theta(self):
+        return np.array(self._itr_start)   # slice.py:113-119 recomputes the very same array
+
+    def _require_sections(self):
+        status = self._arr(_lib.ARR_STATUS)
+        bad = np.nonzero(status & (_lib.ST_EMPTY | _lib.ST_OPEN | _lib.ST_NONMANIFOLD))[0]
+        if len(bad):
+            # the reference fails here too (``None.centroid`` / ``p.area`` on None, slice.py:38,56)
+            raise ValueError(f"planes {bad[:8].tolist()} have no closed section (status {status[bad[:8]].tolist()})")
+
+    # ---- windowing ------------------------------------------------------------------------
+    def _cutoff(self, entity, cutoff: tuple):
+        n = len(entity)
+        lo, hi = int((1 - cutoff[1]) * n), int((1 - cutoff[0]) * n)
+        if self.return_odd and len(entity[lo:hi]) % 2 == 0:
+            hi -= 1
+        return entity[lo:hi]
+
+    def slices(self, cutoff: tuple):
+        return self._cutoff(self._slices, cutoff)
+
+    def centroids(self, cutoff: tuple):
+        return self._cutoff(self._centroids, cutoff)
+
+    def areas1(self, cutoff: tuple):
+        return self._cutoff(self._areas1, cutoff)
+
+    def ixy(self, cutoff: tuple):
+        return self._cutoff(self._ixy, cutoff)
+
+    def ixy_centered(self, cutoff: tuple):
+        return self._cutoff(self._ixy_centered, cutoff)
+
+    def itr(self, cutoff: tuple) -> np.ndarray:
+        return self._cutoff(self._ixy, cutoff)            # sic: slice.py:99-100
+
+    def itr_start(self, cutoff: tuple):
+        return self._cutoff(self._itr_start, cutoff)
+
+    def itr_start_even_theta(self, cutoff: tuple):
+        return self._cutoff(self._itr_start, cutoff)      # sic: slice.py:121-122
+
+    def itr_centered(self, cutoff: tuple):
+        return self._cutoff(self._itr_centered, cutoff)
+
+    def itr_centered_start(self, cutoff: tuple):
+        return self._cutoff(self._itr_centered_start, cutoff)
+
+    def zs(self, cutoff) -> np.ndarray:
+        return self._cutoff(self._zs, cutoff)
+
+    # extra product (not in the reference): ray-cast radius image, see DESIGN.md
+    def radial(self, n_angles: int = 360) -> np.ndarray:
+        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], _lib.OUT_PLANE | _lib.OUT_RADIAL, n_angles)
+        return np.array(res.array(_lib.ARR_RADIAL, 0))
+
+
+def _profile_property(name: str, which: int):
+    def get(self):
+        self._require_sections()
+        return np.array(self._arr(which))
+    get.__name__ = name
+    prop = cached_property(get)
+    prop.__set_name__(GpuSlices, name)
+    return prop
+
+
+for _name, _which in _PROFILE_ARRAYS.items():
+    setattr(GpuSlices, _name, _profile_property(_name, _which))
+
+
+class GpuFullSlices(GpuSlices):
+    def __init__(self, obb, zslice_num=200, interp_num=100, return_odd=False):
+        super().__init__(obb, zslice_num, interp_num, return_odd)
+
+    @cached_property
+    def _zs(self) -> np.ndarray:
+        z = self.obb.mesh.bounds[:, -1]
+        return np.linspace(0.99 * np.max(z), 0.99 * np.min(z), self._zslice_num)
+
+
+class GpuProximalSlices(GpuSlices):
+    def __init__(self, obb, surgical_neck, zslice_num=600, interp_num=512, return_odd=False):
+        # 600 x 512 "must not change": the anatomic-neck CNN input (slice.py:236-237)
+        self.surgical_neck = surgical_neck
+        super().__init__(obb, zslice_num, interp_num, return_odd)
+
+    @cached_property
+    def _zs(self) -> np.ndarray:
+        z = self.obb.mesh.bounds[:, -1]
+        return np.linspace(0.99 * np.max(z), self.surgical_neck.neck_z, self._zslice_num)
+
+
+class GpuDistalSlices(GpuSlices):
+    def __init__(self, obb, zslice_num=200, interp_num=500, return_odd=False):
+        super().__init__(obb, zslice_num, interp_num, return_odd)
+
+    @cached_property
+    def _zs(self) -> np.ndarray:
+        z = self.obb.mesh.bounds[:, -1]
+        return np.linspace(0.99 * np.min(z), 0, self._zslice_num)
+
+
+def run_batch(slices_objects, extra_mask: int = 0):
+    """Fill many slice providers (any mix of bones / sweeps) with ONE backend call.  Objects that
+    share an ``obb`` share the uploaded mesh.  Returns the shared ``SweepResult``."""
+    meshes, mesh_id, sweeps = [], {}, []
+    for s in slices_objects:
+        key = id(s.obb.mesh)
+        if key not in mesh_id:
+            mesh_id[key] = len(meshes)
+            meshes.append(s._mesh_arrays())
+        sweeps.append(s._sweep_spec(mesh_id[key]))
+    res = _lib.sweep_batch(meshes, sweeps, _RUN_MASK | extra_mask)
+    for k, s in enumerate(slices_objects):
+        s._attached = (res, k)
+        s.__dict__.pop("_result", None)
+    return res
+
+
+def install(reference_slice_module) -> None:
+    """Drop-in switch: make ``shoulder.humerus.slice`` resolve to the GPU providers, so that
+    ``bone.Humerus`` (bone.py:116-121) builds them instead of the trimesh-backed ones."""
+    reference_slice_module.FullSlices = GpuFullSlices
+    reference_slice_module.ProximalSlices = GpuProximalSlices
+    reference_slice_module.DistalSlices = GpuDistalSlices

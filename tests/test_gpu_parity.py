@@ -1,0 +1,50 @@
+"""Parity of the CUDA path with the oracle, through the C ABI (needs a B200)."""
+import numpy as np
+import pytest
+
+from shoulder_b200 import meshio
+
+from helpers import compare_sweep
+
+pytestmark = pytest.mark.gpu
+
+
+def _zs(v, n, inset=0.99):
+    return np.linspace(inset * v[:, 2].max(), inset * v[:, 2].min(), n)
+
+
+def test_ellipsoid(gpu_backend):
+    v, f = meshio.icosphere(3, 1.0, scale=(20.0, 30.0, 170.0))
+    rep = compare_sweep(v, f, _zs(v, 64), 100, n_angles=90)
+    assert rep["contours"] == 64 and not rep["h4_exceptions"]
+
+
+def test_torus_two_loops(gpu_backend):
+    v, f = meshio.torus(30.0, 8.0, 64, 32)
+    rep = compare_sweep(v, f, _zs(v, 40, 0.97), 128)
+    assert rep["contours"] > 40            # planes through the hole cut two loops
+
+
+@pytest.mark.parametrize("name", ["humerus_left", "humerus_right", "humerus_left_trab", "humerus_left_flipped"])
+def test_bones_full_sweep(gpu_backend, bone_obbs, name):
+    m = bone_obbs(name).mesh
+    rep = compare_sweep(m.vertices, m.faces, _zs(m.vertices, 200), 100)
+    assert rep["segments"] > 20000
+    assert not rep["h4_exceptions"]
+
+
+def test_bone_proximal_sweep_512(gpu_backend, bone_obbs):
+    m = bone_obbs("humerus_left").mesh
+    z = m.vertices[:, 2]
+    zs = np.linspace(0.99 * z.max(), 0.55 * z.max(), 600)
+    rep = compare_sweep(m.vertices, m.faces, zs, 512, n_angles=360)
+    assert rep["max_rel"] < 1e-9
+
+
+def test_ascending_and_unsorted_heights(gpu_backend, bone_obbs):
+    m = bone_obbs("humerus_right").mesh
+    z = m.vertices[:, 2]
+    zs = np.linspace(0.99 * z.min(), 0.0, 50)                      # ascending, like DistalSlices
+    compare_sweep(m.vertices, m.faces, zs, 500)
+    rng = np.random.default_rng(7)
+    compare_sweep(m.vertices, m.faces, rng.permutation(zs), 64)     # arbitrary order
