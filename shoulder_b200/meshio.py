@@ -256,14 +256,17 @@ def icosphere(levels: int = 2, radius: float = 1.0, scale=(1.0, 1.0, 1.0)):
     return v * np.asarray(scale, dtype=np.float64), f
 
 
-def torus(major: float = 3.0, minor: float = 1.0, nu: int = 48, nv: int = 24):
-    """Genus-1 test solid with its axis along +x, so z planes cut two separate loops."""
+def torus(major: float = 3.0, minor: float = 1.0, nu: int = 48, nv: int = 24, wobble: float = 0.3):
+    """Genus-1 test solid with its axis along +x, so z planes cut two separate loops.  The tube
+    radius varies around the ring (``wobble``) so the two loops of a plane differ in area —
+    an exact tie would leave ``argmax(area)`` (slice.py:55-57) to rounding noise."""
     u = np.linspace(0, 2 * np.pi, nu, endpoint=False)
     w = np.linspace(0, 2 * np.pi, nv, endpoint=False)
     uu, ww = np.meshgrid(u, w, indexing="ij")
-    y = (major + minor * np.cos(ww)) * np.cos(uu)
-    z = (major + minor * np.cos(ww)) * np.sin(uu)
-    x = minor * np.sin(ww)
+    rad = minor * (1.0 + wobble * np.cos(uu + 0.4))
+    y = (major + rad * np.cos(ww)) * np.cos(uu)
+    z = (major + rad * np.cos(ww)) * np.sin(uu)
+    x = rad * np.sin(ww)
     v = np.c_[x.reshape(-1), y.reshape(-1), z.reshape(-1)]
     idx = np.arange(nu * nv).reshape(nu, nv)
     a = idx

@@ -1,0 +1,40 @@
+"""Partitioning of the hot path over the GPUs of one box (one process per GPU).
+
+Every (mesh, plane) pair is independent, so there is no exchange step and no collective on the
+data path: batches shard by bone, a single large mesh shards by contiguous
+plane range (the mesh is replicated, outputs concatenate in plane order)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bones(n_bones: int, rank: int, world: int, cost=None) -> np.ndarray:
+    """Bone ids owned by ``rank``.  Without ``cost`` bones go round-robin; with a per-bone cost
+    (e.g. triangles x planes) they are dealt greedily, heaviest first, to the lightest rank."""
+    if cost is None:
+        return np.arange(rank, n_bones, world, dtype=np.int64)
+    cost = np.asarray(cost, dtype=np.float64)
+    load = np.zeros(world)
+    owner = np.empty(n_bones, dtype=np.int64)
+    for b in np.argsort(-cost, kind="stable"):
+        r = int(np.argmin(load))
+        owner[b] = r
+        load[r] += cost[b]
+    return np.nonzero(owner == rank)[0].astype(np.int64)
+
+
+def shard_planes(n_planes: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous plane range [lo, hi) of ``rank``; ranges tile [0, n_planes) in rank order."""
+    base, rem = divmod(n_planes, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def plane_shard_heights(zs: np.ndarray, rank: int, world: int):
+    """Heights a rank passes to the backend for its plane range.  ``z_orig`` stays the mean of
+    the FULL list (slice.py:18-19), so every rank classifies against the same planes as a
+    single-GPU run and concatenating the per-rank outputs reproduces it bit for bit."""
+    zs = np.asarray(zs, dtype=np.float64)
+    z_orig = float(np.mean(zs))
+    lo, hi = shard_planes(len(zs), rank, world)
+    return z_orig, (zs - z_orig)[lo:hi], (lo, hi)
