@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <type_traits>
@@ -54,6 +55,7 @@ struct Ctx {
     std::vector<PinnedBuf> pinned;
     uint32_t* h_totals = nullptr;          // pinned readback slot
     unsigned long long* h_totals64 = nullptr;
+    double2* angle_tab = nullptr; int angle_n = 0;
 } g;
 
 void* pinned_get(size_t bytes) {
@@ -293,14 +295,15 @@ SHB_API int shb_result_free(shb_result* r) {
     if (!r) return SHB_OK;
     cudaStream_t st = g.stream;
     ShbDev& d = r->d;
-    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.dec, st); dfree(d.sort_off, st);
-    dfree(d.sort_cur, st); dfree(d.cand_off, st); dfree(d.cnt, st); dfree(d.totals, st); dfree(d.totals64, st);
+    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
+    dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.totals, st); dfree(d.totals64, st);
     dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
     dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
     dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
     dfree(d.ct_start, st); dfree(d.ct_len, st); dfree(d.ct_area, st);
     for (int a = 0; a < 6; ++a) dfree(d.prof[a], st);
     dfree(d.radial, st); dfree(d.scratch, st);
+
     dfree(r->d_ct_off, st); dfree(r->d_pt_off, st); dfree(r->d_pts_c, st); dfree(r->d_ctpt_c, st); dfree(r->d_ctarea_c, st);
     void* hp[] = {r->h_nseg, r->h_nent, r->h_sel, r->h_face_index, r->h_status, r->h_seg_off, r->h_ct_off, r->h_pt_off,
                   r->h_bounds, r->h_centroid, r->h_area1, r->h_segments, r->h_pts, r->h_ctarea, r->h_ctpt, r->h_radial,
@@ -336,37 +339,16 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(cudaMemcpyAsync(d_sw, r->sweeps.data(), b->n_sweep * sizeof(ShbSweep), cudaMemcpyHostToDevice, st));
     d.sweep = d_sw;
 
-    CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st));
-    CK(dalloc(&d.inc, G + 1, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.sort_off, G + 1, st));
-    CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cand_off, G + 1, st)); CK(dalloc(&d.cnt, G, st));
+    CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
+    CK(dalloc(&d.inc, G, st)); CK(dalloc(&d.sort_off, G + 1, st)); CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cnt, G, st));
+    CK(dalloc(&d.tile_sum, (G + 4095) / 4096 + 1, st));
     CK(dalloc(&d.totals, 8, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
     CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
     CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
     CK(dalloc(&d.o_sel, 2 * (size_t)G, st));
-    CK(cudaMemsetAsync(d.inc, 0, (G + 1) * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, (G + 1) * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.cnt, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.totals, 0, 8 * sizeof(uint32_t), st));
-
-    { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
-    { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
-    CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(g.h_totals64, d.totals64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));          // the one mid-pipeline sync: sizes of everything downstream
-    const uint32_t M = g.h_totals[SHB_T_M], W = g.h_totals[SHB_T_W], maxcand = g.h_totals[SHB_T_MAXCAND];
-    if (g.h_totals64[0] >= (1ull << 31)) {
-        shb_result* rr = r.release(); cudaFreeAsync(d_sw, st); rr->d.sweep = nullptr; shb_result_free(rr);
-        return fail(SHB_E_CAPACITY, "%llu candidate segments in one batch; split it", g.h_totals64[0]);
-    }
-    r->W = W;
-    CK(dalloc(&d.rec, M, st)); CK(dalloc(&d.hits, W, st));
-    CK(dalloc(&d.face_index, W, st)); CK(dalloc(&d.segments, 4 * (size_t)W, st)); CK(dalloc(&d.pts, 4 * (size_t)W + 4, st));
-    CK(dalloc(&d.ct_start, W, st)); CK(dalloc(&d.ct_len, W, st)); CK(dalloc(&d.ct_area, W, st));
-    const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
-                              SHB_OUT_ITR_CENTERED_START};
-    bool any_prof = false;
-    for (int a = 0; a < 6; ++a)
-        if (outputs_mask & pbit[a]) { CK(dalloc(&d.prof[a], r->prof_total, st)); any_prof = true; }
-    if (outputs_mask & SHB_OUT_RADIAL) { CK(dalloc(&d.radial, r->rad_total, st)); any_prof = true; }
 
     // shared-memory capacities (leave headroom for static shared memory)
     const size_t budget = (g.smem_optin > 8192 ? g.smem_optin - 4096 : 40960);
@@ -378,21 +360,57 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     for (uint32_t step = 1u << 20; step; step >>= 1)
         if (shb_resample_ws_bytes(pcap + step, b->max_interp, (uint32_t)n_angles) <= budget) pcap += step;
     d.resample_cap = pcap;
-    if (maxcand > cap || 2 * (size_t)maxcand + 2 > pcap) {
+    { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
+    { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
+    { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
+    CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st));      // reused as the hit-list cursors
+    { StageTimer t(3); t.stop(shb_launch_intersect(d, 0, st)); }
+    { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
+    CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(g.h_totals64, d.totals64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));          // the one mid-pipeline sync: sizes of everything downstream
+    const uint32_t S = g.h_totals[SHB_T_S], maxcand = g.h_totals[SHB_T_MAXN];
+    if (g.h_totals64[0] >= (1ull << 31)) {
+        shb_result* rr = r.release(); cudaFreeAsync(d_sw, st); rr->d.sweep = nullptr; shb_result_free(rr);
+        return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
+    }
+    r->W = S;
+    CK(dalloc(&d.hits, S, st));
+    CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
+    CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
+    const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
+                              SHB_OUT_ITR_CENTERED_START};
+    bool any_prof = false;
+    for (int a = 0; a < 6; ++a)
+        if (outputs_mask & pbit[a]) { CK(dalloc(&d.prof[a], r->prof_total, st)); any_prof = true; }
+    if (outputs_mask & SHB_OUT_RADIAL) {
+        CK(dalloc(&d.radial, r->rad_total, st)); any_prof = true;
+        // ray directions from the host's libm (what numpy evaluates): theta_k = -pi + (2*pi/A)*k; cached per A
+        if (g.angle_n != n_angles) {
+            std::vector<double> tab(2 * (size_t)n_angles);
+            const double pi = 3.141592653589793, dA = 2.0 * pi / (double)n_angles;
+            for (int k = 0; k < n_angles; ++k) { double th = -pi + dA * (double)k; tab[2 * k] = std::cos(th); tab[2 * k + 1] = std::sin(th); }
+            if (g.angle_tab) cudaFree(g.angle_tab);
+            CK(cudaMalloc(&g.angle_tab, (size_t)n_angles * sizeof(double2)));
+            CK(cudaMemcpy(g.angle_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+            g.angle_n = n_angles;
+        }
+        d.angle_cs = g.angle_tab;
+    }
+    const bool need_scratch = maxcand > cap || 2 * (size_t)maxcand + 2 > pcap;
+    if (need_scratch) {
         size_t s1 = shb_stitch_ws_bytes(maxcand), s2 = shb_resample_ws_bytes(2 * maxcand + 2, b->max_interp, (uint32_t)n_angles);
         d.scratch_stride = (std::max(s1, s2) + 255) & ~(size_t)255;
         CK(dalloc(&d.scratch, d.scratch_stride * (size_t)g.n_sm, st));
     }
 
-    { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
-    { StageTimer t(3); t.stop(shb_launch_intersect(d, M, st)); }
-    { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
+    { StageTimer t(3); t.stop(shb_launch_intersect(d, 1, st)); }
     { StageTimer t(5); t.stop(shb_launch_stitch(d, maxcand, g.n_sm, st)); }
     if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
-    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.dec, st); dfree(d.sort_off, st);
-    dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st); dfree(d.cand_off, st);
+    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
+    dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st);
     dfree(d.cnt, st); dfree(d.scratch, st);
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
     *out = r.release();
@@ -431,6 +449,7 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
     if (rc) return rc;
     bool sync = false;
     if ((mask & SHB_OUT_SEGMENTS) && !r->have_seg) {
+        if (!(r->mask & SHB_OUT_SEGMENTS)) return fail(SHB_E_STATE, "segments / face_index were not in the outputs_mask of the run");
         const size_t S = r->S;
         r->h_face_index = (int32_t*)pinned_get(S * 4); r->h_segments = (double*)pinned_get(S * 32);
         if (!r->h_face_index || !r->h_segments) return fail(SHB_E_NOMEM, "pinned host allocation failed");

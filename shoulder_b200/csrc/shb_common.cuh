@@ -52,15 +52,14 @@ struct ShbDev {
     // ---- per-run scratch
     uint32_t* item_lo;    // [n_item] first sorted plane of the triangle's range
     uint32_t* item_span;  // [n_item]
-    uint32_t* inc;        // [G+1] #triangles whose range starts at plane
-    uint32_t* dec;        // [G+1] #triangles whose range ends before plane
-    uint32_t* sort_off;   // [G+1]
-    uint32_t* sort_cur;   // [G]
-    uint32_t* cand_off;   // [G+1] capacity offsets of the per-plane hit lists
+    uint32_t* inc;        // [G]   #triangles whose range starts at (sorted) plane = counting-sort histogram
+    uint32_t* sort_off;   // [G+1] bucket offsets
+    uint32_t* sort_cur;   // [G]   bucket cursors (scatter), then hit-list cursors (intersect fill)
     uint32_t* cnt;        // [G]   exact hits per sorted plane
-    uint32_t* totals;     // [8]   M, W, maxcand, S, maxn, nbig, ...
-    uint4*    rec;        // [M]   bucketed triangles (face, lo, span, sweep)
-    uint32_t* hits;       // [W]   per-plane lists of global face ids
+    uint32_t* tile_sum;   // [ceil(G/4096)] scan scratch
+    uint32_t* totals;     // [8]   M, -, -, S, maxn, nbig, ...
+    uint4*    rec;        // [n_item] bucketed triangles (face, lo, span, sweep); first M are live
+    uint32_t* hits;       // [S]   per-plane lists of global face ids, caller plane order
     uint32_t* seg_off;    // [G+1] exact segment offsets, original plane order
     uint32_t* big_list;   // [G]   planes too large for shared memory
     // ---- outputs (device)
@@ -81,6 +80,7 @@ struct ShbDev {
     double*   ct_area;    // [S]
     double*   prof[6];    // ixy, ixy_centered, itr, itr_start, itr_centered, itr_centered_start
     double*   radial;
+    const double2* angle_cs;     // [n_angles] (cos, sin) of theta_k = -pi + 2*pi*k/n_angles
     unsigned char* scratch;      // global workspaces for oversized planes
     size_t    scratch_stride;
     uint32_t  n_angles;
@@ -107,7 +107,7 @@ __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
     return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + 64;
 }
 __host__ __device__ inline size_t shb_resample_ws_bytes(uint32_t npts, uint32_t N, uint32_t A) {
-    return 24 * ((size_t)npts + 1) + 32 * (size_t)N + 12 * (size_t)shb_pow2_ge(N) + 8 * (size_t)A + 64;
+    return 32 * ((size_t)npts + 1) + 32 * (size_t)N + 12 * (size_t)shb_pow2_ge(N) + 8 * (size_t)A + 64;
 }
 
 #ifdef __cplusplus
@@ -120,7 +120,7 @@ int shb_launch_prep_mesh(const double* verts_in, const int64_t* faces_in, const 
 int shb_launch_bucket(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_planes(const ShbDev& d, cudaStream_t st);
 int shb_launch_scatter(const ShbDev& d, cudaStream_t st);
-int shb_launch_intersect(const ShbDev& d, uint32_t M, cudaStream_t st);
+int shb_launch_intersect(const ShbDev& d, int fill, cudaStream_t st);
 int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
 int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, int n_sm, cudaStream_t st);
 int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t maxN, int n_sm, cudaStream_t st);

@@ -49,8 +49,9 @@ def _point_in_ring(p, ring) -> bool:
 
 
 class GpuPath2D:
-    def __init__(self, result: "_lib.SweepResult", sweep: int, plane: int, z: float):
+    def __init__(self, result: "_lib.SweepResult", sweep: int, plane: int, z: float, full=None):
         self._res, self._k, self._i, self._z = result, sweep, plane, z
+        self._full = full        # callable -> (SweepResult, sweep) of a run that kept segments / face_index
 
     def _a(self, which):
         return self._res.array(which, self._k)
@@ -133,12 +134,13 @@ class GpuPath2D:
     # ---- what section_multiplane attaches ---------------------------------------------------
     @property
     def metadata(self):
-        off = self._a(_lib.ARR_SEG_OFF)
+        res, k = self._full() if self._full is not None else (self._res, self._k)
+        off = res.array(_lib.ARR_SEG_OFF, k)
         s0, s1 = int(off[self._i]), int(off[self._i + 1])
         to_3d = np.eye(4)
         to_3d[2, 3] = self._z
         return {
-            "face_index": np.array(self._a(_lib.ARR_FACE_INDEX)[s0:s1], dtype=np.int64),
-            "segments": np.array(self._a(_lib.ARR_SEGMENTS)[s0:s1]),
+            "face_index": np.array(res.array(_lib.ARR_FACE_INDEX, k)[s0:s1], dtype=np.int64),
+            "segments": np.array(res.array(_lib.ARR_SEGMENTS, k)[s0:s1]),
             "to_3D": to_3d,
         }

@@ -61,6 +61,13 @@ class GpuSlices:
         res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], _RUN_MASK)
         return res, 0
 
+    @cached_property
+    def _result_full(self):
+        """Second, on-demand run that also keeps mesh_multiplane's own outputs (lines_2D, face_index)."""
+        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)],
+                               _lib.OUT_PLANE | _lib.OUT_SEGMENTS | _lib.OUT_CONTOURS)
+        return res, 0
+
     def _arr(self, which: int) -> np.ndarray:
         res, k = self._result
         return res.array(which, k)
@@ -70,7 +77,7 @@ class GpuSlices:
     def _slices(self):
         res, k = self._result
         status = self._arr(_lib.ARR_STATUS)
-        return [None if status[i] & _lib.ST_EMPTY else GpuPath2D(res, k, i, float(self._zs[i]))
+        return [None if status[i] & _lib.ST_EMPTY else GpuPath2D(res, k, i, float(self._zs[i]), full=lambda: self._result_full)
                 for i in range(len(self._z_incrs))]
 
     @cached_property

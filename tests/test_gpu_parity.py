@@ -48,3 +48,21 @@ def test_ascending_and_unsorted_heights(gpu_backend, bone_obbs):
     compare_sweep(m.vertices, m.faces, zs, 500)
     rng = np.random.default_rng(7)
     compare_sweep(m.vertices, m.faces, rng.permutation(zs), 64)     # arbitrary order
+
+
+def test_fast_mode_matches_full_mode(gpu_backend, bone_obbs):
+    """Without SHB_OUT_SEGMENTS the stitcher skips the canonical sort and evaluates one copy per node;
+    contours, plane records and profiles must not change by a single bit."""
+    from shoulder_b200 import _lib
+    from helpers import run_gpu
+    m = bone_obbs("humerus_left_trab").mesh
+    zs = np.linspace(0.99 * m.vertices[:, 2].max(), 0.99 * m.vertices[:, 2].min(), 300)
+    fast = run_gpu(m.vertices, m.faces, zs, 128, _lib.OUT_PLANE | _lib.OUT_CONTOURS | _lib.OUT_ALL_PROFILES | _lib.OUT_RADIAL, 72)
+    full = run_gpu(m.vertices, m.faces, zs, 128, _lib.OUT_PLANE | _lib.OUT_SEGMENTS | _lib.OUT_CONTOURS | _lib.OUT_ALL_PROFILES | _lib.OUT_RADIAL, 72)
+    for w in (_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_BOUNDS, _lib.ARR_CENTROID, _lib.ARR_SEL, _lib.ARR_CONTOUR_OFF,
+              _lib.ARR_CONTOUR_PT_OFF, _lib.ARR_POINTS, _lib.ARR_IXY, _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START,
+              _lib.ARR_ITR, _lib.ARR_ITR_CENTERED, _lib.ARR_RADIAL):
+        assert np.array_equal(fast.array(w), full.array(w)), w
+    assert np.allclose(fast.array(_lib.ARR_AREA1), full.array(_lib.ARR_AREA1), rtol=1e-13)
+    with pytest.raises(_lib.BackendError):
+        fast.array(_lib.ARR_SEGMENTS)
