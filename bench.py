@@ -99,15 +99,17 @@ def cpu_jobs(meshes, sweeps, angles, max_planes=None):
 # helpers
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons, sampled every 50 ms from before the warm-up to the end of
+    the run; only samples whose arrival time falls inside a timed region are summarised."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows = index, [], None, []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -115,17 +117,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
 
     def stop(self):
         if self.proc:
+            time.sleep(0.12)
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        inside = [r for (t, r) in self.rows if len(r) >= 9 and any(a - 0.06 <= t <= b + 0.06 for a, b in self.windows)]
+        if not inside:                       # region shorter than the sampling period: take every sample of the run
+            inside = [r for (_, r) in self.rows if len(r) >= 9]
+        num = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
+        sm = [num(r[1]) for r in inside if num(r[1]) is not None]
+        mx = [num(r[2]) for r in inside if num(r[2]) is not None]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in inside:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
@@ -246,6 +254,8 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---------------- device-resident leg -------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     batch = _lib.SweepBatch(None, None, packed=packed_pinned)
     counts = None
     for _ in range(args.warmup):
@@ -255,11 +265,10 @@ def run_ours(args, rank, world, local_rank):
             counts = tot
         r.close()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
     _lib.profile_enable(True)
     _lib.profile_read(reset=True)
     barrier()
-    sampler.start()
+    t_dev0 = time.perf_counter()
     launches0 = _lib.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in ev:
@@ -269,8 +278,8 @@ def run_ours(args, rank, world, local_rank):
         b.record(stream)
         r.close()
     barrier()
+    sampler.window(t_dev0, time.perf_counter())
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     stages = _lib.profile_read(reset=True)
     _lib.profile_enable(False)
@@ -296,6 +305,8 @@ def run_ours(args, rank, world, local_rank):
         r.close()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    sampler.window(t0, t0 + e2e_s)
+    clocks = sampler.stop()
 
     # ---------------- reduce over ranks ----------------------------------------------------
     tvals = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -329,14 +340,14 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        jobs = cpu_jobs(meshes[:1], [s for s in sweeps if s[0] == 0], args.angles, max_planes=args.cpu_planes)
-        n_pl = sum(len(j[2]) for j in jobs)
-        t0 = time.perf_counter()
-        for j in jobs:
-            _cpu_one(j)
+        n_pl, nb, t0 = 0, 0, time.perf_counter()
+        while time.perf_counter() - t0 < 12.0 and nb < len(meshes):          # >= ~12 s of CPU work, whole bones
+            for j in cpu_jobs(meshes, [s for s in sweeps if s[0] == nb], args.angles, max_planes=args.cpu_planes):
+                n_pl += _cpu_one(j)
+            nb += 1
         dt = time.perf_counter() - t0
         cpu = {"value": n_pl / dt, "unit": "planes/s", "cores": 1, "kind": "port",
-               "sample": f"bone 0 of the batch, {n_pl} evenly spaced planes of its sweep(s), {dt:.1f} s of single-thread numpy (oracle/)"}
+               "sample": f"first {nb} bone(s) of the batch, {n_pl} planes, {dt:.1f} s of single-thread numpy (oracle/ restatement of the trimesh path)"}
     line = {
         "metric": "planes_per_sec", "value": value, "unit": "planes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
