@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <type_traits>
@@ -360,6 +361,11 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     for (uint32_t step = 1u << 20; step; step >>= 1)
         if (shb_resample_ws_bytes(pcap + step, b->max_interp, (uint32_t)n_angles) <= budget) pcap += step;
     d.resample_cap = pcap;
+    if (const char* f = getenv("SHB_DEBUG_SMEM_CAP")) {      // test hook: push planes onto the global-workspace path
+        uint32_t v = (uint32_t)atoi(f);
+        if (v >= 1) { d.stitch_cap = std::min(d.stitch_cap, v); d.resample_cap = std::min(d.resample_cap, v + 2); }
+    }
+    cap = d.stitch_cap; pcap = d.resample_cap;
     { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
     { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
     { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
@@ -397,9 +403,9 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
         }
         d.angle_cs = g.angle_tab;
     }
-    const bool need_scratch = maxcand > cap || 2 * (size_t)maxcand + 2 > pcap;
+    const bool need_scratch = maxcand > cap || (size_t)maxcand + 1 > pcap;
     if (need_scratch) {
-        size_t s1 = shb_stitch_ws_bytes(maxcand), s2 = shb_resample_ws_bytes(2 * maxcand + 2, b->max_interp, (uint32_t)n_angles);
+        size_t s1 = shb_stitch_ws_bytes(maxcand), s2 = shb_resample_ws_bytes(maxcand + 1, b->max_interp, (uint32_t)n_angles);
         d.scratch_stride = (std::max(s1, s2) + 255) & ~(size_t)255;
         CK(dalloc(&d.scratch, d.scratch_stride * (size_t)g.n_sm, st));
     }

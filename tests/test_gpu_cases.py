@@ -1,0 +1,155 @@
+"""Edge cases, batches, the Python Slices mirror and the full-size property checks (needs a B200)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle.landmarks import axis_angle_deg, canal_axis_obb
+from shoulder_b200 import _lib, meshio
+from shoulder_b200.slice import GpuDistalSlices, GpuFullSlices, GpuProximalSlices, run_batch
+
+from helpers import compare_sweep, rel_err, run_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _cube():
+    v = np.array([[x, y, z] for x in (0.0, 1.0) for y in (0.0, 1.0) for z in (0.0, 1.0)])
+    f = np.array([[0, 2, 3], [0, 3, 1], [4, 5, 7], [4, 7, 6], [0, 1, 5], [0, 5, 4], [2, 6, 7], [2, 7, 3],
+                  [0, 4, 6], [0, 6, 2], [1, 3, 7], [1, 7, 5]])
+    return v, f
+
+
+def test_cube_planes_through_faces_and_vertices(gpu_backend):
+    """sign == 0 cases: coplanar bottom face (code 16 kept, code 6 dropped), coplanar top face (no section),
+    planes that miss the mesh (None), plus the tilted cube whose planes pass exactly through vertices (code 8)."""
+    v, f = _cube()
+    zs = np.array([0.5, 0.0, 1.0, 2.0, -1.0, 0.25])
+    rep = compare_sweep(v, f, zs, 16, expect_all_closed=False)
+    assert rep["segments"] == 8 + 4 + 8
+    d = np.array([1.0, 1.0, 1.0]) / np.sqrt(3)
+    x = np.cross(d, [0, 0, 1.0]); x /= np.linalg.norm(x)
+    r = np.stack([x, np.cross(d, x), d])
+    vr = (v - 0.5) @ r.T
+    lv = np.sort(np.unique(np.round(vr[:, 2], 12)))
+    zs = np.array([lv[1], lv[2], 0.0, 0.5 * (lv[0] + lv[1])])
+    rep = compare_sweep(vr, f, zs, 24, expect_all_closed=False)
+    klass = np.concatenate([p.metadata["klass"] for p in rep["oracle"].paths if p is not None])
+    assert (klass == oracle.trimesh_path.CLASS_VERTEX).any()
+
+
+def test_open_mesh_is_flagged_not_fatal(gpu_backend):
+    v, f = meshio.icosphere(2, 10.0)
+    keep = np.ones(len(f), dtype=bool)
+    keep[np.argsort(v[f].mean(axis=1)[:, 0])[-40:]] = False          # cut a hole at +x
+    zs = np.linspace(8.0, -8.0, 9)
+    res = run_gpu(v, f[keep], zs, 16)
+    status = res.array(_lib.ARR_STATUS)
+    orc = oracle.OracleSlices(v, f[keep], zs, 16, merge="topo")
+    for i, p in enumerate(orc.paths):
+        closed = all(p.entity_closed(k) for k in range(len(p.entities)))
+        assert bool(status[i] & _lib.ST_OPEN) == (not closed), i
+    assert (status & _lib.ST_OPEN).any() and not (status & _lib.ST_OPEN).all()
+
+
+def test_batch_of_bones_and_mixed_sweeps(gpu_backend, bone_obbs):
+    """config-4 shape: several bones, the three default sweeps each (200x100, 200x500, 600x512 scaled down), one call."""
+    names = ["humerus_left", "humerus_left_trab", "humerus_right"]
+    meshes, sweeps, specs = [], [], []
+    for k, name in enumerate(names):
+        m = meshio.synthetic_bone(bone_obbs(name).mesh, 100 + k)
+        m = meshio.PcaObb(m).mesh
+        z = m.vertices[:, 2]
+        meshes.append((m.vertices, m.faces))
+        for zs, n in ((np.linspace(0.99 * z.max(), 0.99 * z.min(), 50), 100), (np.linspace(0.99 * z.min(), 0.0, 40), 500),
+                      (np.linspace(0.99 * z.max(), 0.5 * z.max(), 75), 512)):
+            sweeps.append((k, float(zs.mean()), zs - zs.mean(), n))
+            specs.append((m, zs, n))
+    mask = _lib.OUT_PLANE | _lib.OUT_SEGMENTS | _lib.OUT_CONTOURS | _lib.OUT_ALL_PROFILES
+    res = _lib.sweep_batch(meshes, sweeps, mask)
+    for s, (m, zs, n) in enumerate(specs):
+        rep = compare_sweep(m.vertices, m.faces, zs, n, res=res, sweep=s)
+        assert rep["planes"] == len(zs)
+
+
+def test_python_slices_mirror_and_canal_axis(gpu_backend, bone_obbs):
+    class Neck:
+        neck_z = 60.0
+    obb = bone_obbs("humerus_left")
+    full, dist, prox = GpuFullSlices(obb), GpuDistalSlices(obb), GpuProximalSlices(obb, Neck(), zslice_num=120, interp_num=512)
+    run_batch([full, dist, prox])
+    m = obb.mesh
+    for g, zs in ((full, full._zs), (dist, dist._zs), (prox, prox._zs)):
+        o = oracle.OracleSlices(m.vertices, m.faces, zs, g._interp_num)
+        assert np.array_equal(g._centroids, o.centroids)
+        assert rel_err(g._areas1, o.areas1) < 1e-12
+        for name in ("ixy", "ixy_centered", "itr", "itr_start", "itr_centered", "itr_centered_start"):
+            assert rel_err(getattr(g, "_" + name), getattr(o, name)) < 1e-9, name
+        assert np.array_equal(g.itr((0.2, 0.8)), g.ixy((0.2, 0.8)))                      # slice.py:99-100
+        assert np.array_equal(g.itr_start_even_theta((0.2, 0.8)), g.itr_start((0.2, 0.8)))  # slice.py:121-122
+        p = g.slices((0.35, 0.75))[3]
+        q = o.window(o.paths, (0.35, 0.75))[3]
+        assert np.array_equal(p.centroid, q.centroid) and len(p.entities) == len(q.entities)
+        assert np.array_equal(p.discrete[0], q.discrete[0])
+        assert abs(p.area - q.area) <= 1e-12 * q.area
+        assert np.array_equal(p.metadata["face_index"], q.metadata["face_index"])
+    # final landmark parity that is reachable without the missing models: canal axis (canal.py:40-85), angle budget 0.01 deg
+    o = oracle.OracleSlices(m.vertices, m.faces, full._zs, 100)
+    ax_g = canal_axis_obb(full._centroids, full._zs, obb.z_length)
+    ax_o = canal_axis_obb(o.centroids, full._zs, obb.z_length)
+    assert axis_angle_deg(ax_g, ax_o) < 0.01 and rel_err(ax_g, ax_o) < 1e-9
+
+
+def test_oversized_planes_take_the_global_workspace_path(gpu_backend, bone_obbs):
+    m = bone_obbs("humerus_right").mesh
+    zs = np.linspace(0.99 * m.vertices[:, 2].max(), 0.99 * m.vertices[:, 2].min(), 60)
+    os.environ["SHB_DEBUG_SMEM_CAP"] = "96"            # most planes have > 96 segments
+    try:
+        rep = compare_sweep(m.vertices, m.faces, zs, 100, n_angles=36)
+    finally:
+        del os.environ["SHB_DEBUG_SMEM_CAP"]
+    assert rep["contours"] >= 60
+
+
+def test_half_million_triangles_properties(gpu_backend, bone_obbs):
+    """BASELINE config 3 scale (Loop-subdivided humerus, 519,040 triangles, 8,192 planes): size-independent
+    properties at full size + the oracle on a sample of planes."""
+    base = bone_obbs("humerus_left").mesh
+    v, f = meshio.loop_subdivide(base.vertices, base.faces, 2)
+    assert len(f) == 519040
+    z = v[:, 2]
+    zs = np.linspace(0.99 * z.max(), 0.99 * z.min(), 8192)
+    res = run_gpu(v, f, zs, 360, _lib.OUT_PLANE | _lib.OUT_SEGMENTS | _lib.OUT_CONTOURS | _lib.OUT_IXY | _lib.OUT_ITR_START)
+    status, n_ent, n_seg = res.array(_lib.ARR_STATUS), res.array(_lib.ARR_N_ENT), res.array(_lib.ARR_N_SEG)
+    assert not (status & (_lib.ST_EMPTY | _lib.ST_OPEN | _lib.ST_NONMANIFOLD)).any()       # watertight in, closed out
+    ct_off, ctpt, pts = res.array(_lib.ARR_CONTOUR_OFF), res.array(_lib.ARR_CONTOUR_PT_OFF), res.array(_lib.ARR_POINTS)
+    # every contour closed; points per plane == segments + contours (each node once + closing duplicates)
+    first, last = pts[ctpt[:-1]], pts[ctpt[1:] - 1]
+    assert np.array_equal(first, last)
+    assert np.array_equal(np.diff(ctpt).reshape(-1).sum(), n_seg.sum() + n_ent.sum())
+    # face_index ascending within class blocks => strictly increasing except at <= 2 class boundaries per plane
+    off, fi = res.array(_lib.ARR_SEG_OFF), res.array(_lib.ARR_FACE_INDEX)
+    drops = np.add.reduceat((np.diff(fi) <= 0).astype(np.int64), off[:-1][:-0 or None])[: len(zs)]
+    interior = np.ones(len(fi) - 1, dtype=bool)
+    interior[off[1:-1] - 1] = False                         # ignore plane boundaries
+    assert ((np.diff(fi) <= 0) & interior).sum() == 0       # real bones never touch a vertex: one class per plane
+    # ixy rows are closed polylines; itr_start rows start at their minimum theta
+    ixy, itr = res.array(_lib.ARR_IXY), res.array(_lib.ARR_ITR_START)
+    assert np.array_equal(ixy[:, :, 0], ixy[:, :, -1])
+    assert np.array_equal(itr[:, 0, 0], itr[:, 0, :].min(axis=1))
+    # area1 bounded by the bounding box, areas vary smoothly along the shaft
+    b = res.array(_lib.ARR_BOUNDS)
+    box = (b[:, 1, 0] - b[:, 0, 0]) * (b[:, 1, 1] - b[:, 0, 1])
+    a1 = res.array(_lib.ARR_AREA1)
+    assert (a1 > 0).all() and (a1 <= box * (1 + 1e-12)).all()
+    # oracle on 24 sampled planes of the same sweep (same z_orig => identical planes)
+    idx = np.linspace(5, 8186, 24).astype(int)
+    z_orig = zs.mean()
+    paths = oracle.section_multiplane(v, f, [0, 0, z_orig], [0, 0, 1], (zs - z_orig)[idx], merge="topo")
+    for i, p in zip(idx, paths):
+        assert np.array_equal(fi[off[i]:off[i + 1]], p.metadata["face_index"])
+        c0 = int(ct_off[i])
+        for k, dsc in enumerate(p.discrete):
+            assert np.array_equal(pts[int(ctpt[c0 + k]):int(ctpt[c0 + k + 1])], dsc)
+        assert np.array_equal(res.array(_lib.ARR_CENTROID)[i], p.centroid)
