@@ -191,7 +191,7 @@ def run_reference(args, rank, world):
     value = planes_per_step * args.steps_ref / dt
     used = min(cores, len(jobs))
     sample = (f"{n_bones} bone(s) x {len(jobs) // max(n_bones, 1)} sweep(s), {planes_per_step} planes per step "
-              f"({'every plane' if args.ref_planes is None else f'{args.ref_planes} evenly spaced planes per sweep'}), "
+              f"(at most {args.ref_planes} planes per sweep), "
               f"numpy restatement of the trimesh path, multiprocessing over sweeps")
     line = {
         "impl": "reference", "metric": "planes_per_sec", "value": value, "unit": "planes/s", "n_gpus": args.gpus,
@@ -230,7 +230,10 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.init(local_rank)
-    stream = torch.cuda.current_stream()
+    # an explicit (non-NULL) stream: the library enqueues on it and the torch events below are recorded on it
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     _lib.set_stream(stream.cuda_stream)
 
     bones = args.bones if args.workload != "cfg3" else 1
