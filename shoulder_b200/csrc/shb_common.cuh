@@ -104,7 +104,7 @@ __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
     size_t c1 = 4 * (size_t)shb_pow2_ge(n) + 4 * (size_t)shb_hash_size(n);   // sort keys + hash table
     size_t c2 = 12 * E;                                                       // jump pairs + heads
     size_t c = c1 > c2 ? c1 : c2;
-    return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + 64;
+    return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + n /*lone-vertex signs*/ + 80;
 }
 __host__ __device__ inline size_t shb_resample_ws_bytes(uint32_t npts, uint32_t N, uint32_t A, bool sorted = true) {
     return 24 * ((size_t)npts + 1) + 32 * (size_t)N + (sorted ? 12 * (size_t)shb_pow2_ge(N) : 0) + 8 * (size_t)A + 64;
