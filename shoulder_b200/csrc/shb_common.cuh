@@ -94,9 +94,13 @@ enum { SHB_T_M = 0, SHB_T_W = 1, SHB_T_MAXCAND = 2, SHB_T_S = 3, SHB_T_MAXN = 4,
 
 // bytes of workspace the stitch kernel needs for a plane with n segments
 __host__ __device__ inline uint32_t shb_pow2_ge(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return x <= 1u ? 1u : 1u << (32 - __clz((int)(x - 1u)));
+#else
     uint32_t p = 1;
     while (p < x) p <<= 1;
     return p;
+#endif
 }
 __host__ __device__ inline uint32_t shb_hash_size(uint32_t n) { return shb_pow2_ge(2 * n + n / 2 + 1); }
 __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
@@ -104,7 +108,8 @@ __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
     size_t c1 = 4 * (size_t)shb_pow2_ge(n) + 4 * (size_t)shb_hash_size(n);   // sort keys + hash table
     size_t c2 = 12 * E;                                                       // jump pairs + heads
     size_t c = c1 > c2 ? c1 : c2;
-    return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + n /*lone-vertex signs*/ + 80;
+    return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + n /*lone-vertex signs*/ + 96 +
+           8 * E /*start-node coordinates of the fast path*/;
 }
 __host__ __device__ inline size_t shb_resample_ws_bytes(uint32_t npts, uint32_t N, uint32_t A, bool sorted = true) {
     return 24 * ((size_t)npts + 1) + 32 * (size_t)N + (sorted ? 12 * (size_t)shb_pow2_ge(N) : 0) + 8 * (size_t)A + 64;
