@@ -381,7 +381,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
         return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
     }
     r->W = S;
-    CK(dalloc(&d.hits, S, st));
+    CK(dalloc(&d.hits, (size_t)S + 8, st));      // + slack: TMA copies are widened to 16-byte boundaries
     CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
     CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
     const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
