@@ -309,13 +309,22 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     sampler.window(t0, t0 + e2e_s)
+    # same call with float32 profile / radius outputs (SHB_OUT_F32), reported beside the float64 headline
+    for _ in range(2):
+        _lib.sweep_batch(None, None, mask_e2e | _lib.OUT_F32, args.angles, packed=packed_pinned).close()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    for i in range(args.steps):
+        _lib.sweep_batch(None, None, mask_e2e | _lib.OUT_F32, args.angles, packed=packed_pinned).close()
+    torch.cuda.synchronize()
+    e2e32_s = time.perf_counter() - t1
     clocks = sampler.stop()
 
     # ---------------- reduce over ranks ----------------------------------------------------
-    tvals = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tvals = torch.tensor([ms, e2e_s * 1e3, e2e32_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max = float(tvals[0]), float(tvals[1])
+    ms_max, e2e_ms_max, e2e32_ms_max = float(tvals[0]), float(tvals[1]), float(tvals[2])
     total_planes = planes_per_step * world
     value = total_planes * args.steps / (ms_max * 1e-3)
     e2e_value = total_planes * args.steps / (e2e_ms_max * 1e-3)
@@ -359,7 +368,10 @@ def run_ours(args, rank, world, local_rank):
         "segments_per_step_per_gpu": S, "contours_per_step_per_gpu": Cn,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "planes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_max / args.steps, "bones_per_sec": bones * world * args.steps / (e2e_ms_max * 1e-3)},
+                "ms_per_step": e2e_ms_max / args.steps, "bones_per_sec": bones * world * args.steps / (e2e_ms_max * 1e-3),
+                "outputs": "plane records + ixy + itr_start + itr_centered_start (+ radius image), float64, every plane"},
+        "e2e_f32": {"value": total_planes * args.steps / (e2e32_ms_max * 1e-3), "unit": "planes/s",
+                    "ms_per_step": e2e32_ms_max / args.steps, "note": "same call with SHB_OUT_F32 (float32 profile arrays)"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -385,7 +397,7 @@ def main():
     if args.planes is None:
         args.planes = 8192 if args.workload == "cfg3" else 2048
     if args.workload == "cfg3" and args.cpu_planes is None:
-        args.cpu_planes = 64
+        args.cpu_planes = 512
     if args.workload == "cfg3" and args.ref_planes is None:
         args.ref_planes = 16
     args.warmup = max(args.warmup, 3)

@@ -59,6 +59,8 @@ extern "C" {
 #define SHB_OUT_ITR_CENTERED_START 0x100u  /* slice.py:136-144 */
 #define SHB_OUT_RADIAL             0x200u  /* extra product: ray-cast radius image, n_angles per plane */
 #define SHB_OUT_ALL_PROFILES       0x1F8u
+#define SHB_OUT_F32                0x400u  /* deliver the profile arrays and the radius image as float32 (computed in fp64,
+                                              rounded on store); halves their HBM and PCIe bytes.  north_star tolerance: 1e-5 */
 
 /* array ids for shb_result_array */
 enum shb_array {
@@ -91,6 +93,7 @@ enum shb_array {
 #define SHB_DT_I64 2
 #define SHB_DT_U32 3
 #define SHB_DT_F64 4
+#define SHB_DT_F32 5
 
 /* per-plane status bits */
 #define SHB_ST_EMPTY        0x01u  /* no face crosses the plane: section_multiplane yields None   */

@@ -18,13 +18,14 @@ OUT_PLANE, OUT_SEGMENTS, OUT_CONTOURS = 0x001, 0x002, 0x004
 OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START = 0x008, 0x010, 0x020, 0x040
 OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL = 0x080, 0x100, 0x200
 OUT_ALL_PROFILES = 0x1F8
+OUT_F32 = 0x400
 (ARR_N_SEG, ARR_SEG_OFF, ARR_N_ENT, ARR_STATUS, ARR_BOUNDS, ARR_CENTROID, ARR_AREA1, ARR_SEL, ARR_FACE_INDEX,
  ARR_SEGMENTS, ARR_CONTOUR_OFF, ARR_CONTOUR_PT_OFF, ARR_CONTOUR_AREA, ARR_POINTS, ARR_IXY, ARR_IXY_CENTERED, ARR_ITR,
  ARR_ITR_START, ARR_ITR_CENTERED, ARR_ITR_CENTERED_START, ARR_RADIAL, ARR_COUNT) = range(22)
 ST_EMPTY, ST_OPEN, ST_NONMANIFOLD, ST_RANK_TIE, ST_SPLIT_COPY, ST_GENERAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
 N_STAGES = 7
 STAGE_NAMES = ("bucket", "scan", "scatter", "intersect", "scan2", "stitch", "resample")
-_DTYPES = {1: np.int32, 2: np.int64, 3: np.uint32, 4: np.float64}
+_DTYPES = {1: np.int32, 2: np.int64, 3: np.uint32, 4: np.float64, 5: np.float32}
 
 EXPORTS = (
     "shb_init", "shb_set_stream", "shb_batch_create", "shb_batch_free", "shb_batch_run", "shb_sweep_batch",

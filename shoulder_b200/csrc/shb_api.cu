@@ -125,7 +125,8 @@ struct shb_result {
     uint32_t *h_status = nullptr, *h_seg_off = nullptr, *h_ct_off = nullptr, *h_pt_off = nullptr;
     double *h_bounds = nullptr, *h_centroid = nullptr, *h_area1 = nullptr, *h_segments = nullptr;
     double *h_pts = nullptr, *h_ctarea = nullptr; int64_t* h_ctpt = nullptr;
-    double* h_prof[6] = {}; double* h_radial = nullptr;
+    void* h_prof[6] = {}; void* h_radial = nullptr;
+    size_t esz = 8;                         // bytes per profile / radius element
     std::vector<std::vector<int64_t>> rel;  // per-sweep relative offset arrays handed out
 };
 
@@ -302,8 +303,9 @@ SHB_API int shb_result_free(shb_result* r) {
     dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
     dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
     dfree(d.ct_start, st); dfree(d.ct_len, st); dfree(d.ct_area, st);
-    for (int a = 0; a < 6; ++a) dfree(d.prof[a], st);
-    dfree(d.radial, st); dfree(d.scratch, st);
+    for (int a = 0; a < 6; ++a) if (d.prof[a]) { cudaFreeAsync(d.prof[a], st); d.prof[a] = nullptr; }
+    if (d.radial) { cudaFreeAsync(d.radial, st); d.radial = nullptr; }
+    dfree(d.scratch, st);
 
     dfree(r->d_ct_off, st); dfree(r->d_pt_off, st); dfree(r->d_pts_c, st); dfree(r->d_ctpt_c, st); dfree(r->d_ctarea_c, st);
     void* hp[] = {r->h_nseg, r->h_nent, r->h_sel, r->h_face_index, r->h_status, r->h_seg_off, r->h_ct_off, r->h_pt_off,
@@ -326,6 +328,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     std::unique_ptr<shb_result> r(new shb_result);
     r->batch = b; r->sweeps = b->sweeps; r->G = G; r->mask = outputs_mask; r->n_angles = (uint32_t)n_angles;
     r->prof_total = b->prof_total; r->rel.resize((size_t)b->n_sweep * 3);
+    r->esz = (outputs_mask & SHB_OUT_F32) ? 4 : 8;
     uint64_t rad = 0;
     for (auto& sw : r->sweeps) { sw.rad_off = rad; rad += (uint64_t)sw.n_plane * (uint64_t)n_angles; }
     r->rad_total = rad;
@@ -388,9 +391,9 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
                               SHB_OUT_ITR_CENTERED_START};
     bool any_prof = false;
     for (int a = 0; a < 6; ++a)
-        if (outputs_mask & pbit[a]) { CK(dalloc(&d.prof[a], r->prof_total, st)); any_prof = true; }
+        if (outputs_mask & pbit[a]) { CK(cudaMallocAsync(&d.prof[a], std::max<size_t>(r->prof_total, 1) * r->esz, st)); any_prof = true; }
     if (outputs_mask & SHB_OUT_RADIAL) {
-        CK(dalloc(&d.radial, r->rad_total, st)); any_prof = true;
+        CK(cudaMallocAsync(&d.radial, std::max<size_t>(r->rad_total, 1) * r->esz, st)); any_prof = true;
         // ray directions from the host's libm (what numpy evaluates): theta_k = -pi + (2*pi/A)*k; cached per A
         if (g.angle_n != n_angles) {
             std::vector<double> tab(2 * (size_t)n_angles);
@@ -493,16 +496,16 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
     for (int a = 0; a < 6; ++a)
         if ((mask & pbit[a]) && !r->h_prof[a]) {
             if (!r->d.prof[a]) return fail(SHB_E_STATE, "profile array %d was not in the outputs_mask of the run", a);
-            r->h_prof[a] = (double*)pinned_get(r->prof_total * 8);
+            r->h_prof[a] = pinned_get(r->prof_total * r->esz);
             if (!r->h_prof[a]) return fail(SHB_E_NOMEM, "pinned host allocation failed");
-            CK(cudaMemcpyAsync(r->h_prof[a], r->d.prof[a], r->prof_total * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(r->h_prof[a], r->d.prof[a], r->prof_total * r->esz, cudaMemcpyDeviceToHost, st));
             sync = true;
         }
     if ((mask & SHB_OUT_RADIAL) && !r->h_radial) {
         if (!r->d.radial) return fail(SHB_E_STATE, "radial image was not in the outputs_mask of the run");
-        r->h_radial = (double*)pinned_get(r->rad_total * 8);
+        r->h_radial = pinned_get(r->rad_total * r->esz);
         if (!r->h_radial) return fail(SHB_E_NOMEM, "pinned host allocation failed");
-        CK(cudaMemcpyAsync(r->h_radial, r->d.radial, r->rad_total * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(r->h_radial, r->d.radial, r->rad_total * r->esz, cudaMemcpyDeviceToHost, st));
         sync = true;
     }
     if (sync) CK(cudaStreamSynchronize(st));
@@ -582,11 +585,12 @@ SHB_API const void* shb_result_array(shb_result* r, int32_t which, int32_t sweep
         }
         case SHB_ARR_POINTS: *dtype = SHB_DT_F64; *ndim = 2; shape[0] = (int64_t)r->h_pt_off[p0 + P] - r->h_pt_off[p0]; shape[1] = 2;
             return r->h_pts + 2 * (size_t)r->h_pt_off[p0];
-        case SHB_ARR_RADIAL: *dtype = SHB_DT_F64; *ndim = 2; shape[1] = r->n_angles; return r->h_radial + sw.rad_off;
+        case SHB_ARR_RADIAL: *dtype = r->esz == 4 ? SHB_DT_F32 : SHB_DT_F64; *ndim = 2; shape[1] = r->n_angles;
+            return (const char*)r->h_radial + sw.rad_off * r->esz;
         default: {
             const int a = which - SHB_ARR_IXY;
-            *dtype = SHB_DT_F64; *ndim = 3; shape[1] = 2; shape[2] = (int64_t)N;
-            return r->h_prof[a] + sw.prof_off;
+            *dtype = r->esz == 4 ? SHB_DT_F32 : SHB_DT_F64; *ndim = 3; shape[1] = 2; shape[2] = (int64_t)N;
+            return (const char*)r->h_prof[a] + sw.prof_off * r->esz;
         }
     }
 }

@@ -78,8 +78,8 @@ struct ShbDev {
     uint32_t* ct_start;   // [S] capacity layout: plane p owns [seg_off[p], seg_off[p+1])
     uint32_t* ct_len;     // [S]
     double*   ct_area;    // [S]
-    double*   prof[6];    // ixy, ixy_centered, itr, itr_start, itr_centered, itr_centered_start
-    double*   radial;
+    void*     prof[6];    // ixy, ixy_centered, itr, itr_start, itr_centered, itr_centered_start (f64, or f32 with SHB_OUT_F32)
+    void*     radial;
     const double2* angle_cs;     // [n_angles] (cos, sin) of theta_k = -pi + 2*pi*k/n_angles
     unsigned char* scratch;      // global workspaces for oversized planes
     size_t    scratch_stride;

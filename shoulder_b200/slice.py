@@ -36,6 +36,14 @@ _RUN_MASK = _lib.OUT_PLANE | _lib.OUT_ALL_PROFILES
 class GpuSlices:
     """Common part (reference ``Slices``, slice.py:9-207)."""
 
+    #: dtype of the profile arrays handed back.  float64 mirrors the reference; float32 (computed in fp64 on
+    #: the device, rounded on store) halves the device->host bytes and stays inside north_star's 1e-5 budget.
+    profile_dtype = np.float64
+
+    @classmethod
+    def _run_mask(cls) -> int:
+        return _RUN_MASK | (_lib.OUT_F32 if np.dtype(cls.profile_dtype) == np.float32 else 0)
+
     def __init__(self, obb, zslice_num: int, interp_num: int, return_odd: bool = False):
         self._mesh_oriented_uobb = obb.mesh
         self.obb = obb
@@ -58,7 +66,7 @@ class GpuSlices:
     def _result(self):
         if self._attached is not None:
             return self._attached
-        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], _RUN_MASK)
+        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], self._run_mask())
         return res, 0
 
     @cached_property
@@ -213,7 +221,7 @@ def run_batch(slices_objects, extra_mask: int = 0):
             mesh_id[key] = len(meshes)
             meshes.append(s._mesh_arrays())
         sweeps.append(s._sweep_spec(mesh_id[key]))
-    res = _lib.sweep_batch(meshes, sweeps, _RUN_MASK | extra_mask)
+    res = _lib.sweep_batch(meshes, sweeps, type(slices_objects[0])._run_mask() | extra_mask)
     for k, s in enumerate(slices_objects):
         s._attached = (res, k)
         s.__dict__.pop("_result", None)

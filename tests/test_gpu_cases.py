@@ -153,3 +153,19 @@ def test_half_million_triangles_properties(gpu_backend, bone_obbs):
         for k, dsc in enumerate(p.discrete):
             assert np.array_equal(pts[int(ctpt[c0 + k]):int(ctpt[c0 + k + 1])], dsc)
         assert np.array_equal(res.array(_lib.ARR_CENTROID)[i], p.centroid)
+
+
+def test_float32_profile_outputs_stay_inside_the_north_star_budget(gpu_backend, bone_obbs):
+    """SHB_OUT_F32: same fp64 computation, float32 stores.  Tolerance = north_star's 1e-5 relative."""
+    m = bone_obbs("humerus_left").mesh
+    zs = np.linspace(0.99 * m.vertices[:, 2].max(), 0.99 * m.vertices[:, 2].min(), 128)
+    mask = _lib.OUT_PLANE | _lib.OUT_ALL_PROFILES | _lib.OUT_RADIAL
+    r64 = run_gpu(m.vertices, m.faces, zs, 360, mask, 360)
+    r32 = run_gpu(m.vertices, m.faces, zs, 360, mask | _lib.OUT_F32, 360)
+    for w in (_lib.ARR_IXY, _lib.ARR_IXY_CENTERED, _lib.ARR_ITR, _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED,
+              _lib.ARR_ITR_CENTERED_START, _lib.ARR_RADIAL):
+        a, b = r32.array(w), r64.array(w)
+        assert a.dtype == np.float32 and b.dtype == np.float64 and a.shape == b.shape
+        assert np.array_equal(a, b.astype(np.float32)), w          # identical values, rounded once
+        assert rel_err(a, b) < 1e-5
+    assert np.array_equal(r32.array(_lib.ARR_CENTROID), r64.array(_lib.ARR_CENTROID))     # plane records stay f64
