@@ -169,3 +169,57 @@ def test_float32_profile_outputs_stay_inside_the_north_star_budget(gpu_backend, 
         assert np.array_equal(a, b.astype(np.float32)), w          # identical values, rounded once
         assert rel_err(a, b) < 1e-5
     assert np.array_equal(r32.array(_lib.ARR_CENTROID), r64.array(_lib.ARR_CENTROID))     # plane records stay f64
+
+
+def test_many_and_nested_contours(gpu_backend):
+    """A row of spheres (dozens of contours per plane, ordered by the rank of their start vertex) and a hollow
+    ball (outer shell + inward-facing inner shell: nested loops, Path2D.area = shell minus hole)."""
+    vs, fs, off = [], [], 0
+    rng = np.random.default_rng(11)
+    for k in range(30):
+        v, f = meshio.icosphere(2, 1.0 + 0.02 * k)
+        vs.append(v + np.array([3.1 * (k % 6) + rng.uniform(-0.2, 0.2), 3.3 * (k // 6) + rng.uniform(-0.2, 0.2), rng.uniform(-0.3, 0.3)]))
+        fs.append(f + off); off += len(v)
+    v, f = np.vstack(vs), np.vstack(fs)
+    rep = compare_sweep(v, f, np.linspace(0.8, -0.8, 17), 64, expect_all_closed=True)
+    assert rep["contours"] >= 17 * 25
+    vo, fo = meshio.icosphere(3, 10.0)
+    vi, fi = meshio.icosphere(3, 6.0)
+    v = np.vstack([vo, vi + np.array([0.7, -0.4, 0.2])])
+    f = np.vstack([fo, fi[:, ::-1] + len(vo)])                  # inner surface faces inward
+    zs = np.linspace(9.0, -9.0, 25)
+    rep = compare_sweep(v, f, zs, 90, n_angles=36)
+    orc = rep["oracle"]
+    from shoulder_b200.slice import GpuFullSlices
+
+    class Obb:
+        mesh = meshio.Mesh(v, f)
+    g = GpuFullSlices(Obb(), zslice_num=25, interp_num=90)
+    nested = 0
+    for p, q in zip(g._slices, oracle.OracleSlices(v, f, g._zs, 90).paths):
+        assert abs(p.area - q.area) <= 1e-12 * max(q.area, 1.0)
+        nested += len(q.entities) == 2
+    assert nested >= 10
+
+
+def test_inconsistent_winding_uses_the_two_cycle_path(gpu_backend, bone_obbs):
+    """Flipping the winding of random faces breaks the direction rule of the fast path; results must still
+    equal the oracle's on the same (flipped) input."""
+    m = bone_obbs("humerus_right").mesh
+    f = m.faces.copy()
+    flip = np.random.default_rng(5).random(len(f)) < 0.3
+    f[flip] = f[flip][:, [0, 2, 1]]
+    zs = np.linspace(0.99 * m.vertices[:, 2].max(), 0.99 * m.vertices[:, 2].min(), 80)
+    compare_sweep(m.vertices, f, zs, 100)
+    from shoulder_b200 import _lib as L
+    fast = run_gpu(m.vertices, f, zs, 100, L.OUT_PLANE | L.OUT_CONTOURS | L.OUT_IXY)
+    full = run_gpu(m.vertices, f, zs, 100, L.OUT_PLANE | L.OUT_SEGMENTS | L.OUT_CONTOURS | L.OUT_IXY)
+    for w in (L.ARR_POINTS, L.ARR_CONTOUR_PT_OFF, L.ARR_IXY, L.ARR_CENTROID):
+        assert np.array_equal(fast.array(w), full.array(w))
+
+
+def test_duplicate_and_unsorted_heights(gpu_backend):
+    v, f = meshio.icosphere(3, 1.0, scale=(20.0, 30.0, 170.0))
+    zs = np.array([10.0, -50.0, 10.0, 120.0, 0.0, 0.0, 169.9, -169.9, 500.0])
+    rep = compare_sweep(v, f, zs, 50, expect_all_closed=False)
+    assert rep["contours"] == 8
