@@ -41,7 +41,7 @@ int fail(int code, const char* fmt, ...) {
 struct PinnedBuf { void* p; size_t size; bool used; };
 
 struct Ctx {
-    std::mutex mu;
+    std::recursive_mutex mu;     // every entry point takes it: one caller at a time per process
     bool inited = false;
     int device = 0, n_sm = 148;
     size_t smem_optin = 0;
@@ -137,7 +137,7 @@ SHB_API int shb_abi_version(void) { return SHB_ABI_VERSION; }
 SHB_API int64_t shb_launch_count(void) { return g.launches; }
 
 SHB_API int shb_init(int device) {
-    std::lock_guard<std::mutex> lk(g.mu);
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (g.inited) {
         if (device != g.device) return fail(SHB_E_STATE, "already initialised on device %d", g.device);
         return SHB_OK;
@@ -167,14 +167,17 @@ SHB_API int shb_init(int device) {
 }
 
 SHB_API int shb_set_stream(void* cuda_stream) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own;
     return SHB_OK;
 }
 
-SHB_API int shb_profile_enable(int on) { g.profile = on != 0; return SHB_OK; }
+SHB_API int shb_profile_enable(int on) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu); g.profile = on != 0; return SHB_OK; }
 
 SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launches[SHB_N_STAGES], int reset) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     for (auto& p : g.pending) {
         CK(cudaEventSynchronize(p.b));
         float ms = 0.f;
@@ -193,6 +196,7 @@ SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launch
 }
 
 SHB_API int shb_batch_free(shb_batch* b) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!b) return SHB_OK;
     cudaStream_t st = g.stream;
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
@@ -204,6 +208,7 @@ SHB_API int shb_batch_free(shb_batch* b) {
 SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
                      const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
                      const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_batch** out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     if (!out) return fail(SHB_E_INVALID, "out is null");
     *out = nullptr;
@@ -217,7 +222,8 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     if (nv >= (int64_t)1 << 31 || nf >= (int64_t)1 << 30) return fail(SHB_E_CAPACITY, "too many vertices/faces in one batch");
     if (G64 <= 0 || G64 >= (int64_t)1 << 31) return fail(SHB_E_CAPACITY, "plane count %lld out of range", (long long)G64);
 
-    std::unique_ptr<shb_batch> b(new shb_batch);
+    struct BatchDel { void operator()(shb_batch* p) const { shb_batch_free(p); } };
+    std::unique_ptr<shb_batch, BatchDel> b(new shb_batch);
     b->n_mesh = n_mesh; b->n_sweep = n_sweep; b->n_vert = nv; b->n_face = nf; b->G = (uint32_t)G64;
     b->sweeps.resize(n_sweep);
     std::vector<uint32_t> item_off(n_sweep + 1, 0);
@@ -288,12 +294,13 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     CK(cudaMemcpyAsync(g.h_totals, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st); dfree(d_bad, st);
     CK(cudaStreamSynchronize(st));          // host staging vectors go out of scope below
-    if (g.h_totals[0]) { shb_batch_free(b.release()); return fail(SHB_E_INVALID, "face index out of range for its mesh"); }
+    if (g.h_totals[0]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
     *out = b.release();
     return SHB_OK;
 }
 
 SHB_API int shb_result_free(shb_result* r) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!r) return SHB_OK;
     cudaStream_t st = g.stream;
     ShbDev& d = r->d;
@@ -306,7 +313,7 @@ SHB_API int shb_result_free(shb_result* r) {
     for (int a = 0; a < 6; ++a) if (d.prof[a]) { cudaFreeAsync(d.prof[a], st); d.prof[a] = nullptr; }
     if (d.radial) { cudaFreeAsync(d.radial, st); d.radial = nullptr; }
     dfree(d.scratch, st);
-
+    if (d.sweep) { cudaFreeAsync(const_cast<ShbSweep*>(d.sweep), st); d.sweep = nullptr; }
     dfree(r->d_ct_off, st); dfree(r->d_pt_off, st); dfree(r->d_pts_c, st); dfree(r->d_ctpt_c, st); dfree(r->d_ctarea_c, st);
     void* hp[] = {r->h_nseg, r->h_nent, r->h_sel, r->h_face_index, r->h_status, r->h_seg_off, r->h_ct_off, r->h_pt_off,
                   r->h_bounds, r->h_centroid, r->h_area1, r->h_segments, r->h_pts, r->h_ctarea, r->h_ctpt, r->h_radial,
@@ -317,6 +324,7 @@ SHB_API int shb_result_free(shb_result* r) {
 }
 
 SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles, shb_result** out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     if (!b || !out) return fail(SHB_E_INVALID, "null batch/out");
     *out = nullptr;
@@ -325,7 +333,8 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     if (!(outputs_mask & SHB_OUT_RADIAL)) n_angles = 0;
     cudaStream_t st = g.stream;
     const uint32_t G = b->G;
-    std::unique_ptr<shb_result> r(new shb_result);
+    struct ResultDel { void operator()(shb_result* p) const { shb_result_free(p); } };
+    std::unique_ptr<shb_result, ResultDel> r(new shb_result);
     r->batch = b; r->sweeps = b->sweeps; r->G = G; r->mask = outputs_mask; r->n_angles = (uint32_t)n_angles;
     r->prof_total = b->prof_total; r->rel.resize((size_t)b->n_sweep * 3);
     r->esz = (outputs_mask & SHB_OUT_F32) ? 4 : 8;
@@ -379,10 +388,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(cudaMemcpyAsync(g.h_totals64, d.totals64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));          // the one mid-pipeline sync: sizes of everything downstream
     const uint32_t S = g.h_totals[SHB_T_S], maxcand = g.h_totals[SHB_T_MAXN];
-    if (g.h_totals64[0] >= (1ull << 31)) {
-        shb_result* rr = r.release(); cudaFreeAsync(d_sw, st); rr->d.sweep = nullptr; shb_result_free(rr);
-        return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
-    }
+    if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
     r->W = S;
     CK(dalloc(&d.hits, (size_t)S + 8, st));      // + slack: TMA copies are widened to 16-byte boundaries
     CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
@@ -452,6 +458,7 @@ static int fetch_plane(shb_result* r) {
 }
 
 SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!r) return fail(SHB_E_INVALID, "null result");
     cudaStream_t st = g.stream;
     int rc = fetch_plane(r);
@@ -513,6 +520,7 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
 }
 
 SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n_seg, int64_t* n_contour, int64_t* n_point) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     shb_result* r = const_cast<shb_result*>(r_);
     if (!r) return fail(SHB_E_INVALID, "null result");
     int rc = fetch_plane(r);
@@ -530,6 +538,7 @@ SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n
 }
 
 SHB_API const void* shb_result_array(shb_result* r, int32_t which, int32_t sweep, int64_t shape[4], int32_t* ndim, int32_t* dtype) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!r || !shape || !ndim || !dtype) { fail(SHB_E_INVALID, "null argument"); return nullptr; }
     if (sweep < 0 || sweep >= (int32_t)r->sweeps.size()) { fail(SHB_E_INVALID, "sweep %d out of range", sweep); return nullptr; }
     uint32_t need = SHB_OUT_PLANE;
@@ -599,6 +608,7 @@ SHB_API int shb_sweep_batch(int32_t n_mesh, const double* verts, const int64_t* 
                     const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
                     const double* heights, const int64_t* height_off, const int32_t* interp_num, uint32_t outputs_mask,
                     int32_t n_angles, shb_result** out) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
     shb_batch* b = nullptr;
     int rc = shb_batch_create(n_mesh, verts, vert_off, faces, face_off, n_sweep, sweep_mesh, z_orig, heights, height_off, interp_num, &b);
     if (rc) return rc;
