@@ -139,9 +139,7 @@ class SweepResult:
             return np.zeros(shp, dtype=dtype)
         buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
         buf._shb_owner = self            # arr.base -> buf -> self keeps the pinned memory alive
-        arr = np.frombuffer(buf, dtype=dtype).reshape(shp)
-        arr.flags.writeable = False
-        return arr
+        return np.frombuffer(buf, dtype=dtype).reshape(shp)   # a view, like the reference's cached arrays
 
     def fetch(self, mask: int) -> None:
         check(load().shb_result_fetch(self._h, mask))
@@ -211,10 +209,18 @@ class SweepBatch:
             pass
 
 
-def sweep_batch(meshes, sweeps, outputs_mask: int, n_angles: int = 0, packed=None) -> SweepResult:
-    """One-call host-to-host form (``shb_sweep_batch``)."""
+def sweep_batch(meshes, sweeps, outputs_mask: int, n_angles: int = 0, packed=None, lazy: bool = False) -> SweepResult:
+    """One-call host-to-host form (``shb_sweep_batch``).  ``lazy=True`` computes everything in
+    ``outputs_mask`` on the device but copies an array to the host only when it is first asked for
+    (``shb_batch_create`` + ``shb_batch_run``; the inputs are released right after the kernels are enqueued)."""
     init(_inited if _inited is not None else 0)
     a = packed if packed is not None else _pack(meshes, sweeps)
+    if lazy:
+        batch = SweepBatch(None, None, packed=a)
+        res = batch.run(outputs_mask, n_angles)
+        res._keep = None
+        batch.close()                     # stream ordered: the enqueued kernels still see the inputs
+        return res
     r = C.c_void_p()
     check(load().shb_sweep_batch(len(a[1]) - 1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), len(a[4]), _ptr(a[4]),
                                  _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), outputs_mask, n_angles, C.byref(r)))

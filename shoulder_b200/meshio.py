@@ -44,7 +44,11 @@ class Mesh:
 
     @property
     def bounds(self) -> np.ndarray:
-        return np.array([self.vertices.min(axis=0), self.vertices.max(axis=0)])
+        b = getattr(self, "_bounds", None)          # cached like trimesh's; reset by apply_transform
+        if b is None or self._bounds_of is not self.vertices:
+            b = np.array([self.vertices.min(axis=0), self.vertices.max(axis=0)])
+            self._bounds, self._bounds_of = b, self.vertices
+        return b
 
     def copy(self) -> "Mesh":
         return Mesh(self.vertices.copy(), self.faces.copy())

@@ -66,7 +66,7 @@ class GpuSlices:
     def _result(self):
         if self._attached is not None:
             return self._attached
-        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], self._run_mask())
+        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], self._run_mask(), lazy=True)
         return res, 0
 
     @cached_property
@@ -91,7 +91,7 @@ class GpuSlices:
     @cached_property
     def _centroids(self):
         self._require_sections()
-        return np.array(self._arr(_lib.ARR_CENTROID))
+        return self._arr(_lib.ARR_CENTROID)
 
     @cached_property
     def _centroids_repeated(self):
@@ -100,7 +100,7 @@ class GpuSlices:
     @cached_property
     def _areas1(self):
         self._require_sections()
-        area = np.array(self._arr(_lib.ARR_AREA1))
+        area = self._arr(_lib.ARR_AREA1)
         n_ent = self._arr(_lib.ARR_N_ENT)
         # one entity: slice.py:59 asks Path2D.area; identical to the polygon's own area.
         # several entities: slice.py:55-57 takes the largest closed polygon — what the device stored.
@@ -112,11 +112,14 @@ class GpuSlices:
         return np.array(self._itr_start)   # slice.py:113-119 recomputes the very same array
 
     def _require_sections(self):
+        if self.__dict__.get("_sections_ok"):
+            return
         status = self._arr(_lib.ARR_STATUS)
         bad = np.nonzero(status & (_lib.ST_EMPTY | _lib.ST_OPEN | _lib.ST_NONMANIFOLD))[0]
         if len(bad):
             # the reference fails here too (``None.centroid`` / ``p.area`` on None, slice.py:38,56)
             raise ValueError(f"planes {bad[:8].tolist()} have no closed section (status {status[bad[:8]].tolist()})")
+        self._sections_ok = True
 
     # ---- windowing ------------------------------------------------------------------------
     def _cutoff(self, entity, cutoff: tuple):
@@ -168,7 +171,7 @@ class GpuSlices:
 def _profile_property(name: str, which: int):
     def get(self):
         self._require_sections()
-        return np.array(self._arr(which))
+        return self._arr(which)              # view of the result's pinned buffer (no host copy)
     get.__name__ = name
     prop = cached_property(get)
     prop.__set_name__(GpuSlices, name)
@@ -221,7 +224,7 @@ def run_batch(slices_objects, extra_mask: int = 0):
             mesh_id[key] = len(meshes)
             meshes.append(s._mesh_arrays())
         sweeps.append(s._sweep_spec(mesh_id[key]))
-    res = _lib.sweep_batch(meshes, sweeps, type(slices_objects[0])._run_mask() | extra_mask)
+    res = _lib.sweep_batch(meshes, sweeps, type(slices_objects[0])._run_mask() | extra_mask, lazy=True)
     for k, s in enumerate(slices_objects):
         s._attached = (res, k)
         s.__dict__.pop("_result", None)
