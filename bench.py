@@ -162,8 +162,8 @@ def stage_alg_bytes(stage: str, c: dict) -> float:
         return 8 * items + 16 * c["M"]
     if stage == "intersect":
         return 16 * c["M"] + 16 * T + 8 * V + 8 * P + 4 * S
-    if stage == "stitch":       # hit list + mesh once in; face_index, segments, closed contours, plane records out
-        return 4 * S + 16 * T + 32 * V + (4 + 32) * S + 16 * (S + C) + 20 * C + 164 * P
+    if stage == "stitch":       # hit list + mesh once in; closed contours + plane records out (+ face_index, segments when requested)
+        return 4 * S + 16 * T + 32 * V + (36 * S if c.get("full") else 0) + 16 * (S + C) + 20 * C + 164 * P
     if stage == "resample":     # chosen outlines in; k profile arrays + radius image out
         return 16 * (S + C) + 8 * c["k"] * 2 * PN + 8 * A + 88 * P
     return 8 * P * 6
@@ -350,9 +350,16 @@ def run_ours(args, rank, world, local_rank):
     peak, peak_kind = hbm_peak()
     alg = stage_alg_bytes(dom, c)
     achieved = alg / (dom_ms * 1e-3) / 1e9
-    pipeline_alg = 24 * V + 12 * T + (4 + 32 + 16) * S + 16 * Cn + 8 * k_prof * 2 * PN + 8 * PA + 76 * P
+    # whole step: inputs once + the outputs this run delivers (intermediates such as hit lists and contour points are not credited)
+    pipeline_alg = 24 * V + 12 * T + 8 * k_prof * 2 * PN + 8 * PA + 76 * P
+    traffic = None
+    tfile = ROOT / "profiles" / "r1e_traffic.json"
+    if tfile.exists() and args.workload == "cfg2" and bones == 32 and args.planes == 2048 and args.interp == 360 and args.angles == 360:
+        for name, rec in json.loads(tfile.read_text())["kernels"].items():     # ncu --set full capture of this very command
+            if name.startswith("k_" + dom) and not name.endswith("<0>"):
+                traffic = rec["traffic_bytes"]
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg, "ms_per_launch": dom_ms,
+                "frac": achieved / peak, "traffic": traffic, "alg_bytes_per_launch": alg, "ms_per_launch": dom_ms,
                 "stage_ms_per_step": {n: stages[n][0] / args.steps for n in stages},
                 "pipeline": {"alg_bytes_per_step": pipeline_alg, "achieved": pipeline_alg / (ms_max / args.steps * 1e-3) / 1e9,
                              "frac": pipeline_alg / (ms_max / args.steps * 1e-3) / 1e9 / peak}}
