@@ -41,7 +41,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    extra = os.environ.get("SHB_NVCC_EXTRA", "").split()          # experiments only
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
