@@ -295,15 +295,24 @@ def run_ours(args, rank, world, local_rank):
     _lib.profile_enable(False)
 
     # ---------------- end-to-end leg (public host call) -----------------------------------
+    # the batch is handed over as `e2e_chunks` groups of whole bones (pinned host arrays); the library overlaps
+    # each group's device->host copy with the next group's upload + kernels.  Every step moves every input byte
+    # host->device and every output byte device->host.
     mask_e2e = mask_dev
+    chunks, first = _lib.split_packed(packed_pinned, args.e2e_chunks)
+    chunks = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in c) for c in chunks]
+
+    def e2e_call(mask):
+        return _lib.sweep_batch_pipelined(chunks, first, mask, args.angles)
+
     for _ in range(max(2, args.warmup)):
-        r = _lib.sweep_batch(None, None, mask_e2e, args.angles, packed=packed_pinned)
+        r = e2e_call(mask_e2e)
         r.close()
     barrier()
     d2h = 0
     t0 = time.perf_counter()
     for i in range(args.steps):
-        r = _lib.sweep_batch(None, None, mask_e2e, args.angles, packed=packed_pinned)
+        r = e2e_call(mask_e2e)
         if i == 0:
             for s in range(r.n_sweep):
                 for w in (_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_STATUS, _lib.ARR_SEL, _lib.ARR_BOUNDS, _lib.ARR_CENTROID,
@@ -318,11 +327,11 @@ def run_ours(args, rank, world, local_rank):
     sampler.window(t0, t0 + e2e_s)
     # same call with float32 profile / radius outputs (SHB_OUT_F32), reported beside the float64 headline
     for _ in range(2):
-        _lib.sweep_batch(None, None, mask_e2e | _lib.OUT_F32, args.angles, packed=packed_pinned).close()
+        e2e_call(mask_e2e | _lib.OUT_F32).close()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     for i in range(args.steps):
-        _lib.sweep_batch(None, None, mask_e2e | _lib.OUT_F32, args.angles, packed=packed_pinned).close()
+        e2e_call(mask_e2e | _lib.OUT_F32).close()
     torch.cuda.synchronize()
     e2e32_s = time.perf_counter() - t1
     clocks = sampler.stop()
@@ -386,7 +395,8 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "planes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_max / args.steps, "bones_per_sec": bones * world * args.steps / (e2e_ms_max * 1e-3),
-                "outputs": "plane records + ixy + itr_start + itr_centered_start (+ radius image), float64, every plane"},
+                "outputs": "plane records + ixy + itr_start + itr_centered_start (+ radius image), float64, every plane",
+                "call": f"shoulder_b200._lib.sweep_batch_pipelined, {len(chunks)} groups of bones"},
         "e2e_f32": {"value": total_planes * args.steps / (e2e32_ms_max * 1e-3), "unit": "planes/s",
                     "ms_per_step": e2e32_ms_max / args.steps, "note": "same call with SHB_OUT_F32 (float32 profile arrays)"},
         "gpu_launches": int(launches), "clocks": clocks,
@@ -410,6 +420,7 @@ def main():
     ap.add_argument("--cpu-planes", type=int, default=None, help="planes per sweep in the cpu_baseline sample")
     ap.add_argument("--ref-planes", type=int, default=None, help="planes per sweep in one reference-arm step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="groups of bones the e2e call pipelines (D2H of one overlaps compute of the next)")
     args = ap.parse_args()
     if args.planes is None:
         args.planes = 8192 if args.workload == "cfg3" else 2048

@@ -225,3 +225,69 @@ def sweep_batch(meshes, sweeps, outputs_mask: int, n_angles: int = 0, packed=Non
     check(load().shb_sweep_batch(len(a[1]) - 1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), len(a[4]), _ptr(a[4]),
                                  _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), outputs_mask, n_angles, C.byref(r)))
     return SweepResult(r, len(a[4]))
+
+
+class PipelinedResult:
+    """Results of :func:`sweep_batch_pipelined`: one ``SweepResult`` per chunk, addressed by global sweep index."""
+
+    def __init__(self, parts, first_sweep):
+        self.parts, self._first = parts, first_sweep
+        self.n_sweep = first_sweep[-1]
+
+    def _locate(self, sweep: int):
+        c = int(np.searchsorted(self._first, sweep, side="right")) - 1
+        return self.parts[c], sweep - int(self._first[c])
+
+    def array(self, which: int, sweep: int = 0) -> np.ndarray:
+        part, k = self._locate(sweep)
+        return part.array(which, k)
+
+    def totals(self):
+        out = {}
+        for p in self.parts:
+            for k, v in p.totals().items():
+                out[k] = out.get(k, 0) + v
+        return out
+
+    def close(self):
+        for p in self.parts:
+            p.close()
+
+
+def split_packed(packed, n_chunks: int):
+    """Cuts a packed batch (see :func:`_pack`) into ``n_chunks`` batches of whole meshes.  Sweeps must be grouped
+    by mesh in ascending mesh order (what :func:`_pack` produces from per-bone lists)."""
+    verts, voff, faces, foff, smesh, zo, hts, hoff, interp = packed
+    n_mesh = len(voff) - 1
+    n_chunks = max(1, min(n_chunks, n_mesh))
+    assert (np.diff(smesh) >= 0).all(), "sweeps must be grouped by mesh"
+    cuts = np.linspace(0, n_mesh, n_chunks + 1).astype(np.int64)
+    chunks, first = [], [0]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        s0, s1 = int(np.searchsorted(smesh, a, side="left")), int(np.searchsorted(smesh, b, side="left"))
+        chunks.append((verts[voff[a]:voff[b]], voff[a:b + 1] - voff[a], faces[foff[a]:foff[b]], foff[a:b + 1] - foff[a],
+                       (smesh[s0:s1] - a).astype(np.int32), zo[s0:s1], hts[hoff[s0]:hoff[s1]], hoff[s0:s1 + 1] - hoff[s0],
+                       interp[s0:s1]))
+        first.append(s1)
+    return chunks, np.array(first, dtype=np.int64)
+
+
+def sweep_batch_pipelined(chunks, first_sweep, outputs_mask: int, n_angles: int = 0) -> PipelinedResult:
+    """Host-to-host call for a batch pre-cut into chunks (:func:`split_packed`): chunk i+1 is uploaded and
+    computed while chunk i's outputs travel back over PCIe (the library copies on its own stream).  The
+    device->host transfer dominates a large batch (16 bytes per sample), so hiding everything else behind
+    it is the whole gain."""
+    init(_inited if _inited is not None else 0)
+    parts, prev = [], None
+    for c in chunks:
+        batch = SweepBatch(None, None, packed=c)
+        res = batch.run(outputs_mask, n_angles)
+        res._keep = None
+        batch.close()
+        if prev is not None:
+            prev.fetch(outputs_mask)
+            parts.append(prev)
+        prev = res
+    prev.fetch(outputs_mask)
+    parts.append(prev)
+    return PipelinedResult(parts, first_sweep)

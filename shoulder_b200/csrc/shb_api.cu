@@ -46,6 +46,7 @@ struct Ctx {
     int device = 0, n_sm = 148;
     size_t smem_optin = 0;
     cudaStream_t own = nullptr, stream = nullptr;
+    cudaStream_t copy = nullptr;           // device->host copies run here so they overlap the next batch's kernels
     int64_t launches = 0;
     bool profile = false;
     double stage_ms[SHB_N_STAGES] = {};
@@ -116,6 +117,7 @@ struct shb_result {
     uint64_t prof_total = 0, rad_total = 0;
     uint32_t W = 0;                         // capacity of the per-segment arrays
     ShbDev d = {};                          // device pointers owned by the result
+    cudaEvent_t done = nullptr;             // recorded on the compute stream when the result's kernels are enqueued
     uint32_t* d_ct_off = nullptr; uint32_t* d_pt_off = nullptr;
     double* d_pts_c = nullptr; int64_t* d_ctpt_c = nullptr; double* d_ctarea_c = nullptr;
     // host (pinned) copies, filled lazily
@@ -156,6 +158,7 @@ SHB_API int shb_init(int device) {
     g.smem_optin = prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
     g.stream = g.own;
+    CK(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
@@ -319,6 +322,7 @@ SHB_API int shb_result_free(shb_result* r) {
                   r->h_bounds, r->h_centroid, r->h_area1, r->h_segments, r->h_pts, r->h_ctarea, r->h_ctpt, r->h_radial,
                   r->h_prof[0], r->h_prof[1], r->h_prof[2], r->h_prof[3], r->h_prof[4], r->h_prof[5]};
     for (void* p : hp) if (p) pinned_put(p);
+    if (r->done) cudaEventDestroy(r->done);
     delete r;
     return SHB_OK;
 }
@@ -428,13 +432,16 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st);
     dfree(d.cnt, st); dfree(d.scratch, st);
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
+    CK(cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming));
+    CK(cudaEventRecord(r->done, st));
     *out = r.release();
     return SHB_OK;
 }
 
 static int fetch_plane(shb_result* r) {
     if (r->have_plane) return SHB_OK;
-    cudaStream_t st = g.stream;
+    cudaStream_t st = g.copy;
+    if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
     const size_t G = r->G;
     auto grab = [&](auto** hp, const void* dp, size_t bytes) -> int {
         *hp = reinterpret_cast<std::remove_pointer_t<decltype(hp)>>(pinned_get(bytes));
@@ -460,9 +467,10 @@ static int fetch_plane(shb_result* r) {
 SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!r) return fail(SHB_E_INVALID, "null result");
-    cudaStream_t st = g.stream;
+    cudaStream_t st = g.copy, cst = g.stream;
     int rc = fetch_plane(r);
     if (rc) return rc;
+    if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
     bool sync = false;
     if ((mask & SHB_OUT_SEGMENTS) && !r->have_seg) {
         if (!(r->mask & SHB_OUT_SEGMENTS)) return fail(SHB_E_STATE, "segments / face_index were not in the outputs_mask of the run");
@@ -478,15 +486,17 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
         ShbDev d = r->d;
         ShbSweep* d_sw = nullptr;                       // compaction does not read sweeps, but keep ShbDev whole
         (void)d_sw;
-        CK(dalloc(&r->d_ct_off, G + 1, st)); CK(dalloc(&r->d_pt_off, G + 1, st));
-        g.launches += shb_launch_scan_contours(d, r->d_ct_off, r->d_pt_off, st);
-        CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CK(dalloc(&r->d_ct_off, G + 1, cst)); CK(dalloc(&r->d_pt_off, G + 1, cst));
+        g.launches += shb_launch_scan_contours(d, r->d_ct_off, r->d_pt_off, cst);
+        CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cst));
+        CK(cudaStreamSynchronize(cst));
         r->n_cont = g.h_totals[SHB_T_NCONT]; r->n_pts = g.h_totals[SHB_T_NPTS];
-        CK(dalloc(&r->d_pts_c, 2 * (size_t)r->n_pts, st)); CK(dalloc(&r->d_ctpt_c, (size_t)r->n_cont + 1, st));
-        CK(dalloc(&r->d_ctarea_c, r->n_cont, st));
-        g.launches += shb_launch_compact(d, r->d_ct_off, r->d_pt_off, r->d_pts_c, r->d_ctpt_c, r->d_ctarea_c, st);
+        CK(dalloc(&r->d_pts_c, 2 * (size_t)r->n_pts, cst)); CK(dalloc(&r->d_ctpt_c, (size_t)r->n_cont + 1, cst));
+        CK(dalloc(&r->d_ctarea_c, r->n_cont, cst));
+        g.launches += shb_launch_compact(d, r->d_ct_off, r->d_pt_off, r->d_pts_c, r->d_ctpt_c, r->d_ctarea_c, cst);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(r->done, cst));
+        CK(cudaStreamWaitEvent(st, r->done, 0));
         r->h_ct_off = (uint32_t*)pinned_get((G + 1) * 4); r->h_pt_off = (uint32_t*)pinned_get((G + 1) * 4);
         r->h_pts = (double*)pinned_get((size_t)r->n_pts * 16); r->h_ctpt = (int64_t*)pinned_get(((size_t)r->n_cont + 1) * 8);
         r->h_ctarea = (double*)pinned_get((size_t)r->n_cont * 8);

@@ -223,3 +223,23 @@ def test_duplicate_and_unsorted_heights(gpu_backend):
     zs = np.array([10.0, -50.0, 10.0, 120.0, 0.0, 0.0, 169.9, -169.9, 500.0])
     rep = compare_sweep(v, f, zs, 50, expect_all_closed=False)
     assert rep["contours"] == 8
+
+
+def test_pipelined_host_call_equals_the_single_call(gpu_backend, bone_obbs):
+    meshes, sweeps = [], []
+    for k, name in enumerate(["humerus_left", "humerus_right", "humerus_left_trab", "humerus_left_flipped", "humerus_right"]):
+        m = meshio.PcaObb(meshio.synthetic_bone(bone_obbs(name).mesh, 40 + k)).mesh
+        z = m.vertices[:, 2]
+        meshes.append((m.vertices, m.faces))
+        for zs, n in ((np.linspace(0.99 * z.max(), 0.99 * z.min(), 64), 90), (np.linspace(0.99 * z.min(), 0.0, 33), 120)):
+            sweeps.append((k, float(zs.mean()), zs - zs.mean(), n))
+    mask = _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_ITR_START | _lib.OUT_ITR_CENTERED_START | _lib.OUT_RADIAL | _lib.OUT_CONTOURS
+    packed = _lib._pack(meshes, sweeps)
+    one = _lib.sweep_batch(None, None, mask, 45, packed=packed)
+    chunks, first = _lib.split_packed(packed, 3)
+    piped = _lib.sweep_batch_pipelined(chunks, first, mask, 45)
+    assert piped.n_sweep == len(sweeps)
+    for s in range(len(sweeps)):
+        for w in (_lib.ARR_N_SEG, _lib.ARR_CENTROID, _lib.ARR_AREA1, _lib.ARR_IXY, _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START,
+                  _lib.ARR_RADIAL, _lib.ARR_POINTS, _lib.ARR_CONTOUR_PT_OFF):
+            assert np.array_equal(one.array(w, s), piped.array(w, s)), (s, w)
