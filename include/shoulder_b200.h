@@ -118,6 +118,8 @@ SHB_API int shb_set_stream(void* cuda_stream);
  *   faces  (sum T,3) i64 mesh-local vertex ids (as trimesh holds them); face_off [n_mesh+1]
  *   sweep k slices mesh sweep_mesh[k] with the planes  z = z_orig[k] + heights[height_off[k] .. height_off[k+1])
  *   and resamples each outline to interp_num[k] points.
+ * The upload is only enqueued: verts / faces must stay valid until the first shb_batch_run on the batch returns
+ * (or the batch is freed); an out-of-range face index is reported by that run (SHB_E_INVALID).
  * Replaces the argument set of slice.py:24-28 plus Slices.__init__ (slice.py:10-19). */
 SHB_API int shb_batch_create(int32_t n_mesh,
                      const double* verts, const int64_t* vert_off,
@@ -147,6 +149,11 @@ SHB_API int shb_sweep_batch(int32_t n_mesh,
 
 /* Bring the arrays selected by `mask` to pinned host memory (device -> host copy + sync). */
 SHB_API int shb_result_fetch(shb_result* result, uint32_t mask);
+
+/* Same, without waiting: the copies are enqueued on the library's copy stream (behind the result's kernels) and the
+ * call returns; the next shb_result_fetch / shb_result_array / shb_result_totals / shb_result_free on this result
+ * waits for them.  Lets the transfer of one batch overlap the upload and kernels of the next.  Not for contours. */
+SHB_API int shb_result_fetch_async(shb_result* result, uint32_t mask);
 
 /* Borrow one array of one sweep.  shape[0..ndim) is filled, *dtype gets a SHB_DT_* code.
  * Returns NULL (and sets the error) if the array was not computed; fetches it if needed. */

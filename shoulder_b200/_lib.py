@@ -29,7 +29,7 @@ _DTYPES = {1: np.int32, 2: np.int64, 3: np.uint32, 4: np.float64, 5: np.float32}
 
 EXPORTS = (
     "shb_init", "shb_set_stream", "shb_batch_create", "shb_batch_free", "shb_batch_run", "shb_sweep_batch",
-    "shb_result_fetch", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
+    "shb_result_fetch", "shb_result_fetch_async", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
     "shb_profile_read", "shb_launch_count", "shb_last_error", "shb_abi_version",
 )
 
@@ -60,6 +60,7 @@ def load() -> C.CDLL:
     lib.shb_batch_run.argtypes = [p, u32, i32, pp]
     lib.shb_sweep_batch.argtypes = [i32, p, p, p, p, i32, p, p, p, p, p, u32, i32, pp]
     lib.shb_result_fetch.argtypes = [p, u32]
+    lib.shb_result_fetch_async.argtypes = [p, u32]
     lib.shb_result_array.argtypes = [p, i32, i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     lib.shb_result_array.restype = C.c_void_p
     lib.shb_result_totals.argtypes = [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
@@ -144,6 +145,10 @@ class SweepResult:
     def fetch(self, mask: int) -> None:
         check(load().shb_result_fetch(self._h, mask))
 
+    def fetch_async(self, mask: int) -> None:
+        """Enqueue the device->host copies and return; any later access waits for them."""
+        check(load().shb_result_fetch_async(self._h, mask & ~OUT_CONTOURS))
+
     def totals(self):
         v = [C.c_int64() for _ in range(4)]
         check(load().shb_result_totals(self._h, *[C.byref(x) for x in v]))
@@ -187,6 +192,7 @@ class SweepBatch:
         init(_inited if _inited is not None else 0)
         a = packed if packed is not None else _pack(meshes, sweeps)
         self.n_sweep = len(a[4])
+        self._inputs = a                  # the upload is asynchronous: keep the host arrays alive
         h = C.c_void_p()
         check(load().shb_batch_create(len(a[1]) - 1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), self.n_sweep,
                                       _ptr(a[4]), _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), C.byref(h)))
@@ -278,16 +284,14 @@ def sweep_batch_pipelined(chunks, first_sweep, outputs_mask: int, n_angles: int 
     device->host transfer dominates a large batch (16 bytes per sample), so hiding everything else behind
     it is the whole gain."""
     init(_inited if _inited is not None else 0)
-    parts, prev = [], None
+    parts = []
     for c in chunks:
         batch = SweepBatch(None, None, packed=c)
         res = batch.run(outputs_mask, n_angles)
         res._keep = None
         batch.close()
-        if prev is not None:
-            prev.fetch(outputs_mask)
-            parts.append(prev)
-        prev = res
-    prev.fetch(outputs_mask)
-    parts.append(prev)
+        res.fetch_async(outputs_mask)        # copy stream: starts as soon as this group's kernels finish
+        parts.append(res)
+    for res in parts:
+        res.fetch(outputs_mask)              # wait (and fetch what the async form does not cover)
     return PipelinedResult(parts, first_sweep)

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cmath>
 #include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <memory>
 #include <type_traits>
@@ -75,6 +76,22 @@ void pinned_put(void* p) {
     for (auto& b : g.pinned) if (b.p == p) { b.used = false; return; }
 }
 
+// host->device copy of a library-owned (pageable) array through a pinned staging buffer: a pageable
+// cudaMemcpyAsync serialises with transfers in flight on other streams, which would stall the pipelined call
+struct Staging {
+    std::vector<void*> bufs;
+    cudaError_t copy(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+        if (bytes == 0) return cudaSuccess;
+        void* p = pinned_get(bytes);
+        if (!p) return cudaErrorMemoryAllocation;
+        std::memcpy(p, src, bytes);
+        bufs.push_back(p);
+        return cudaMemcpyAsync(dst, p, bytes, cudaMemcpyHostToDevice, st);
+    }
+    void release() { for (void* p : bufs) pinned_put(p); bufs.clear(); }      // call after the stream has been synchronised
+    ~Staging() { release(); }
+};
+
 template <class T> cudaError_t dalloc(T** p, size_t n, cudaStream_t st) {
     return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T), st);
 }
@@ -108,6 +125,9 @@ struct shb_batch {
     ShbSweep* d_sweep = nullptr; uint32_t* d_item_off = nullptr;
     double* h_sorted = nullptr; double* h_orig = nullptr;
     uint32_t *plane_out = nullptr, *plane_in = nullptr, *plane_sweep = nullptr;
+    uint32_t* d_bad = nullptr;             // set by K0 when a face names a vertex outside its mesh; checked at the first run
+    Staging* stage = nullptr;              // pinned copies of the library-built arrays, held until the upload has executed
+    bool checked = false;
 };
 
 struct shb_result {
@@ -122,6 +142,7 @@ struct shb_result {
     double* d_pts_c = nullptr; int64_t* d_ctpt_c = nullptr; double* d_ctarea_c = nullptr;
     // host (pinned) copies, filled lazily
     bool have_plane = false, have_seg = false, have_cont = false;
+    bool pending = false;                   // copies enqueued on the copy stream, not yet waited for
     uint32_t S = 0, n_cont = 0, n_pts = 0;
     int32_t *h_nseg = nullptr, *h_nent = nullptr, *h_sel = nullptr, *h_face_index = nullptr;
     uint32_t *h_status = nullptr, *h_seg_off = nullptr, *h_ct_off = nullptr, *h_pt_off = nullptr;
@@ -163,8 +184,8 @@ SHB_API int shb_init(int device) {
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
-    CK(cudaMallocHost(&g.h_totals, 8 * sizeof(uint32_t)));
-    CK(cudaMallocHost(&g.h_totals64, 2 * sizeof(unsigned long long)));
+    CK(cudaHostAlloc(&g.h_totals, 8 * sizeof(uint32_t), cudaHostAllocMapped));       // written by k_publish, read after a stream sync
+    CK(cudaHostAlloc(&g.h_totals64, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
     g.inited = true;
     return SHB_OK;
 }
@@ -202,6 +223,8 @@ SHB_API int shb_batch_free(shb_batch* b) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!b) return SHB_OK;
     cudaStream_t st = g.stream;
+    if (b->stage) { cudaStreamSynchronize(st); delete b->stage; b->stage = nullptr; }
+    dfree(b->d_bad, st);
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
     dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st);
     delete b;
@@ -273,31 +296,38 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     b->n_item = (uint32_t)items; b->prof_total = prof;
 
     cudaStream_t st = g.stream;
-    double* raw_v = nullptr; int64_t* raw_f = nullptr; int64_t *d_voff = nullptr, *d_foff = nullptr; uint32_t* d_bad = nullptr;
+    const bool dbg = getenv("SHB_DEBUG_TIMING") != nullptr;
+    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    double T0 = now();
+    double* raw_v = nullptr; int64_t* raw_f = nullptr; int64_t *d_voff = nullptr, *d_foff = nullptr;
     CK(dalloc(&raw_v, 3 * (size_t)nv, st)); CK(dalloc(&raw_f, 3 * (size_t)nf, st));
-    CK(dalloc(&d_voff, n_mesh + 1, st)); CK(dalloc(&d_foff, n_mesh + 1, st)); CK(dalloc(&d_bad, 1, st));
+    CK(dalloc(&d_voff, n_mesh + 1, st)); CK(dalloc(&d_foff, n_mesh + 1, st)); CK(dalloc(&b->d_bad, 1, st));
     CK(dalloc(&b->vert, nv, st)); CK(dalloc(&b->vz, nv, st)); CK(dalloc(&b->face, nf, st));
     CK(dalloc(&b->d_sweep, n_sweep, st)); CK(dalloc(&b->d_item_off, n_sweep + 1, st));
     CK(dalloc(&b->h_sorted, G64, st)); CK(dalloc(&b->h_orig, G64, st));
     CK(dalloc(&b->plane_out, G64, st)); CK(dalloc(&b->plane_in, G64, st)); CK(dalloc(&b->plane_sweep, G64, st));
+    double T1 = now();
     CK(cudaMemcpyAsync(raw_v, verts, 3 * (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(raw_f, faces, 3 * (size_t)nf * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_voff, vert_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_foff, face_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(d_bad, 0, sizeof(uint32_t), st));
-    CK(cudaMemcpyAsync(b->d_sweep, b->sweeps.data(), n_sweep * sizeof(ShbSweep), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->d_item_off, item_off.data(), (n_sweep + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->h_sorted, hs.data(), G64 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->h_orig, ho.data(), G64 * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->plane_out, pout.data(), G64 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->plane_in, pin.data(), G64 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b->plane_sweep, psw.data(), G64 * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, d_bad, st);
+    CK(cudaMemsetAsync(b->d_bad, 0, sizeof(uint32_t), st));
+    b->stage = new Staging;
+    Staging& stage = *b->stage;
+    CK(stage.copy(b->d_sweep, b->sweeps.data(), n_sweep * sizeof(ShbSweep), st));
+    CK(stage.copy(b->d_item_off, item_off.data(), (n_sweep + 1) * sizeof(uint32_t), st));
+    CK(stage.copy(b->h_sorted, hs.data(), G64 * sizeof(double), st));
+    CK(stage.copy(b->h_orig, ho.data(), G64 * sizeof(double), st));
+    CK(stage.copy(b->plane_out, pout.data(), G64 * sizeof(uint32_t), st));
+    CK(stage.copy(b->plane_in, pin.data(), G64 * sizeof(uint32_t), st));
+    CK(stage.copy(b->plane_sweep, psw.data(), G64 * sizeof(uint32_t), st));
+    double T2 = now();
+    g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, b->d_bad, st);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(g.h_totals, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st); dfree(d_bad, st);
-    CK(cudaStreamSynchronize(st));          // host staging vectors go out of scope below
-    if (g.h_totals[0]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
+    dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st);
+    // no host synchronisation here: the upload and K0 are only enqueued.  verts / faces must stay valid until the
+    // first shb_batch_run on this batch returns (it synchronises); the face-index range check is reported there.
+    if (dbg) fprintf(stderr, "[shb] create: alloc %.3f  h2d-enqueue %.3f  launch+free %.3f ms\n", T1 - T0, T2 - T1, now() - T2);
     *out = b.release();
     return SHB_OK;
 }
@@ -305,6 +335,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
 SHB_API int shb_result_free(shb_result* r) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!r) return SHB_OK;
+    if (r->pending) { cudaStreamSynchronize(g.copy); r->pending = false; }
     cudaStream_t st = g.stream;
     ShbDev& d = r->d;
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
@@ -353,7 +384,8 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     // sweep descriptors carry the radial offsets of this run
     ShbSweep* d_sw = nullptr;
     CK(dalloc(&d_sw, b->n_sweep, st));
-    CK(cudaMemcpyAsync(d_sw, r->sweeps.data(), b->n_sweep * sizeof(ShbSweep), cudaMemcpyHostToDevice, st));
+    Staging stage;
+    CK(stage.copy(d_sw, r->sweeps.data(), b->n_sweep * sizeof(ShbSweep), st));
     d.sweep = d_sw;
 
     CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
@@ -366,6 +398,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.cnt, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.totals, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaMemcpyAsync(d.totals + SHB_T_W, b->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));   // slot 1: bad-face flag
 
     // shared-memory capacities (leave headroom for static shared memory)
     const size_t budget = (g.smem_optin > 8192 ? g.smem_optin - 4096 : 40960);
@@ -388,12 +421,14 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st));      // reused as the hit-list cursors
     { StageTimer t(3); t.stop(shb_launch_intersect(d, 0, st)); }
     { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
-    CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(g.h_totals64, d.totals64, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    g.launches += shb_launch_publish(d.totals, 8, d.totals64, g.h_totals, g.h_totals64, st);
     CK(cudaStreamSynchronize(st));          // the one mid-pipeline sync: sizes of everything downstream
+    stage.release();
+    if (b->stage) { delete b->stage; b->stage = nullptr; }      // the batch upload has executed too
+    if (g.h_totals[SHB_T_W]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
     const uint32_t S = g.h_totals[SHB_T_S], maxcand = g.h_totals[SHB_T_MAXN];
     if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
-    r->W = S;
+    r->W = S; r->S = S;
     CK(dalloc(&d.hits, (size_t)S + 8, st));      // + slack: TMA copies are widened to 16-byte boundaries
     CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
     CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
@@ -458,15 +493,32 @@ static int fetch_plane(shb_result* r) {
     if ((rc = grab(&r->h_centroid, r->d.o_centroid, G * 16))) return rc;
     if ((rc = grab(&r->h_area1, r->d.o_area1, G * 8))) return rc;
     if ((rc = grab(&r->h_seg_off, r->d.seg_off, (G + 1) * 4))) return rc;
-    CK(cudaStreamSynchronize(st));
-    r->S = r->h_seg_off[G];
-    r->have_plane = true;
+    r->have_plane = true; r->pending = true;
     return SHB_OK;
 }
+
+static int finish_fetch(shb_result* r) {
+    if (r->pending) { CK(cudaStreamSynchronize(g.copy)); r->pending = false; }
+    return SHB_OK;
+}
+
+static int enqueue_fetch(shb_result* r, uint32_t mask);
 
 SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!r) return fail(SHB_E_INVALID, "null result");
+    int rc = enqueue_fetch(r, mask);
+    return rc ? rc : finish_fetch(r);
+}
+
+SHB_API int shb_result_fetch_async(shb_result* r, uint32_t mask) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!r) return fail(SHB_E_INVALID, "null result");
+    if (mask & SHB_OUT_CONTOURS) return fail(SHB_E_INVALID, "contours need a size readback; fetch them with shb_result_fetch");
+    return enqueue_fetch(r, mask);
+}
+
+static int enqueue_fetch(shb_result* r, uint32_t mask) {
     cudaStream_t st = g.copy, cst = g.stream;
     int rc = fetch_plane(r);
     if (rc) return rc;
@@ -479,7 +531,7 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
         if (!r->h_face_index || !r->h_segments) return fail(SHB_E_NOMEM, "pinned host allocation failed");
         CK(cudaMemcpyAsync(r->h_face_index, r->d.face_index, S * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(r->h_segments, r->d.segments, S * 32, cudaMemcpyDeviceToHost, st));
-        r->have_seg = true; sync = true;
+        r->have_seg = true; sync = true; r->pending = true;
     }
     if ((mask & SHB_OUT_CONTOURS) && !r->have_cont) {
         const size_t G = r->G;
@@ -488,7 +540,7 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
         (void)d_sw;
         CK(dalloc(&r->d_ct_off, G + 1, cst)); CK(dalloc(&r->d_pt_off, G + 1, cst));
         g.launches += shb_launch_scan_contours(d, r->d_ct_off, r->d_pt_off, cst);
-        CK(cudaMemcpyAsync(g.h_totals, d.totals, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, cst));
+        g.launches += shb_launch_publish(d.totals, 8, nullptr, g.h_totals, nullptr, cst);
         CK(cudaStreamSynchronize(cst));
         r->n_cont = g.h_totals[SHB_T_NCONT]; r->n_pts = g.h_totals[SHB_T_NPTS];
         CK(dalloc(&r->d_pts_c, 2 * (size_t)r->n_pts, cst)); CK(dalloc(&r->d_ctpt_c, (size_t)r->n_cont + 1, cst));
@@ -506,7 +558,7 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
         CK(cudaMemcpyAsync(r->h_pts, r->d_pts_c, (size_t)r->n_pts * 16, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(r->h_ctpt, r->d_ctpt_c, ((size_t)r->n_cont + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(r->h_ctarea, r->d_ctarea_c, (size_t)r->n_cont * 8, cudaMemcpyDeviceToHost, st));
-        r->have_cont = true; sync = true;
+        r->have_cont = true; sync = true; r->pending = true;
     }
     const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
                               SHB_OUT_ITR_CENTERED_START};
@@ -516,16 +568,16 @@ SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
             r->h_prof[a] = pinned_get(r->prof_total * r->esz);
             if (!r->h_prof[a]) return fail(SHB_E_NOMEM, "pinned host allocation failed");
             CK(cudaMemcpyAsync(r->h_prof[a], r->d.prof[a], r->prof_total * r->esz, cudaMemcpyDeviceToHost, st));
-            sync = true;
+            sync = true; r->pending = true;
         }
     if ((mask & SHB_OUT_RADIAL) && !r->h_radial) {
         if (!r->d.radial) return fail(SHB_E_STATE, "radial image was not in the outputs_mask of the run");
         r->h_radial = pinned_get(r->rad_total * r->esz);
         if (!r->h_radial) return fail(SHB_E_NOMEM, "pinned host allocation failed");
         CK(cudaMemcpyAsync(r->h_radial, r->d.radial, r->rad_total * r->esz, cudaMemcpyDeviceToHost, st));
-        sync = true;
+        sync = true; r->pending = true;
     }
-    if (sync) CK(cudaStreamSynchronize(st));
+    (void)sync;
     return SHB_OK;
 }
 
@@ -535,6 +587,7 @@ SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n
     if (!r) return fail(SHB_E_INVALID, "null result");
     int rc = fetch_plane(r);
     if (rc) return rc;
+    if ((rc = finish_fetch(r))) return rc;
     if (n_plane) *n_plane = r->G;
     if (n_seg) *n_seg = r->S;
     if (n_contour || n_point) {

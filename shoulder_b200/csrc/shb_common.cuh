@@ -132,6 +132,8 @@ int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t maxN, int n_
 int shb_launch_compact(const ShbDev& d, const uint32_t* ct_off, const uint32_t* pt_off,
                        double* pts_out, int64_t* ctpt_out, double* ctarea_out, cudaStream_t st);
 int shb_launch_scan_contours(const ShbDev& d, uint32_t* ct_off, uint32_t* pt_off, cudaStream_t st);
+int shb_launch_publish(const uint32_t* src, int n, const unsigned long long* src64, uint32_t* dst_host,
+                       unsigned long long* dst64_host, cudaStream_t st);
 #ifdef __cplusplus
 }
 #endif

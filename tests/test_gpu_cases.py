@@ -240,6 +240,22 @@ def test_pipelined_host_call_equals_the_single_call(gpu_backend, bone_obbs):
     piped = _lib.sweep_batch_pipelined(chunks, first, mask, 45)
     assert piped.n_sweep == len(sweeps)
     for s in range(len(sweeps)):
-        for w in (_lib.ARR_N_SEG, _lib.ARR_CENTROID, _lib.ARR_AREA1, _lib.ARR_IXY, _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START,
+        for w in (_lib.ARR_N_SEG, _lib.ARR_CENTROID, _lib.ARR_IXY, _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START,
                   _lib.ARR_RADIAL, _lib.ARR_POINTS, _lib.ARR_CONTOUR_PT_OFF):
             assert np.array_equal(one.array(w, s), piped.array(w, s)), (s, w)
+        # multi-contour planes sum their areas with shared-memory atomics: reproducible to rounding, not to the bit
+        assert np.allclose(one.array(_lib.ARR_AREA1, s), piped.array(_lib.ARR_AREA1, s), rtol=1e-13)
+
+
+def test_invalid_inputs_fail_loudly(gpu_backend):
+    v, f = meshio.icosphere(1, 1.0)
+    bad = f.copy(); bad[3, 1] = len(v) + 5
+    with pytest.raises(_lib.BackendError, match="face index out of range"):
+        _lib.sweep_batch([(v, bad)], [(0, 0.0, np.linspace(-0.5, 0.5, 4), 8)], _lib.OUT_PLANE)
+    with pytest.raises(_lib.BackendError):
+        _lib.sweep_batch([(v, f)], [(0, 0.0, np.linspace(-0.5, 0.5, 4), 1)], _lib.OUT_PLANE)        # interp_num < 2
+    with pytest.raises(_lib.BackendError):
+        _lib.sweep_batch([(v, f)], [(2, 0.0, np.linspace(-0.5, 0.5, 4), 8)], _lib.OUT_PLANE)        # sweep names a missing mesh
+    # the library is still usable afterwards
+    res = _lib.sweep_batch([(v, f)], [(0, 0.0, np.linspace(-0.5, 0.5, 4), 8)], _lib.OUT_PLANE | _lib.OUT_IXY)
+    assert (res.array(_lib.ARR_N_ENT) == 1).all()
