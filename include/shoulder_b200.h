@@ -66,7 +66,7 @@ extern "C" {
 enum shb_array {
     SHB_ARR_N_SEG = 0,        /* int32  [P]        segments on the plane                                */
     SHB_ARR_SEG_OFF,          /* int64  [P+1]      offset of the plane's segments, sweep-relative       */
-    SHB_ARR_N_ENT,            /* int32  [P]        len(Path2D.entities)                    slice.py:53,70 */
+    SHB_ARR_N_ENT,            /* int32  [P]        len(Path2D.entities): closed contours + open chains  slice.py:53,70 */
     SHB_ARR_STATUS,           /* uint32 [P]        SHB_ST_* bits                                         */
     SHB_ARR_BOUNDS,           /* f64    [P,2,2]    Path2D.bounds                                         */
     SHB_ARR_CENTROID,         /* f64    [P,2]      Path2D.centroid                         slice.py:34-39 */
@@ -97,7 +97,8 @@ enum shb_array {
 
 /* per-plane status bits */
 #define SHB_ST_EMPTY        0x01u  /* no face crosses the plane: section_multiplane yields None   */
-#define SHB_ST_OPEN         0x02u  /* some contour does not close (mesh not watertight there)      */
+#define SHB_ST_OPEN         0x02u  /* open chain(s) on the plane (mesh not watertight there): counted in N_ENT, no
+                                      contour; closed contours of the same plane are still assembled              */
 #define SHB_ST_NONMANIFOLD  0x04u  /* a node has more than two incident segments                   */
 #define SHB_ST_RANK_TIE     0x08u  /* two distinct nodes share a rounded-coordinate hash (H4-i)    */
 #define SHB_ST_SPLIT_COPY   0x10u  /* two copies of one node round differently (H4-ii)             */

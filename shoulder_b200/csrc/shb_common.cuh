@@ -27,13 +27,13 @@ struct ShbPlaneMeta {
     double   centroid[2]; // bounds midpoint           (Path2D.centroid, slice.py:38)
     double   area1;       // slice.py:49-60
     uint32_t n_seg;
-    uint32_t n_ent;       // len(Path2D.entities)
+    uint32_t n_ent;       // closed contours of the plane (entities that form a path)
     uint32_t status;      // SHB_ST_*
     uint32_t sel_contour; // contour the outline is taken from (slice.py:70-76)
     uint32_t sel_start;   // its first point, relative to the plane's point region
     uint32_t sel_len;     // its point count including the closing duplicate
     uint32_t n_pts;       // points written for the plane (closing duplicates included)
-    uint32_t pad;
+    uint32_t n_open;      // open chains: entities without a contour; len(Path2D.entities) = n_ent + n_open
 };
 
 struct ShbDev {

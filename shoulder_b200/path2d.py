@@ -90,6 +90,10 @@ class GpuPath2D:
             idx = np.r_[np.arange(first, first + m - 1), first]
             out.append(_Entity(idx))
             first += m - 1
+        for _ in range(n - len(out)):                 # open chains (non-watertight input): counted, no geometry
+            e = _Entity(np.zeros(0, dtype=np.int64))
+            e.closed = False
+            out.append(e)
         return out
 
     @property

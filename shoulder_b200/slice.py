@@ -115,7 +115,8 @@ class GpuSlices:
         if self.__dict__.get("_sections_ok"):
             return
         status = self._arr(_lib.ARR_STATUS)
-        bad = np.nonzero(status & (_lib.ST_EMPTY | _lib.ST_OPEN | _lib.ST_NONMANIFOLD))[0]
+        no_outline = self._arr(_lib.ARR_SEL)[:, 1] == 0          # no closed contour to resample
+        bad = np.nonzero((status & (_lib.ST_EMPTY | _lib.ST_NONMANIFOLD)).astype(bool) | no_outline)[0]
         if len(bad):
             # the reference fails here too (``None.centroid`` / ``p.area`` on None, slice.py:38,56)
             raise ValueError(f"planes {bad[:8].tolist()} have no closed section (status {status[bad[:8]].tolist()})")

@@ -65,12 +65,16 @@ def compare_sweep(vertices, faces, zs, interp_num, res=None, sweep=0, n_angles=0
         closed = all(p.entity_closed(k) for k in range(len(p.entities)))
         if not closed:
             assert status[i] & (_lib.ST_OPEN | _lib.ST_NONMANIFOLD), f"plane {i}: open/non-manifold not flagged"
-            continue
-        assert not (status[i] & (_lib.ST_OPEN | _lib.ST_NONMANIFOLD)), f"plane {i}: status {status[i]}"
-        # --- connectivity, contour order, start vertex, orientation: exact
+            if status[i] & _lib.ST_NONMANIFOLD:
+                continue
+        else:
+            assert not (status[i] & (_lib.ST_OPEN | _lib.ST_NONMANIFOLD)), f"plane {i}: status {status[i]}"
+        # --- connectivity, contour order, start vertex, orientation: exact (closed contours; open chains carry none)
         disc = p.discrete
         c0, c1 = int(ct_off[i]), int(ct_off[i + 1])
-        assert c1 - c0 == len(p.entities) == n_ent[i], f"plane {i}: {c1 - c0} contours vs {len(p.entities)}"
+        assert c1 - c0 == len(disc), f"plane {i}: {c1 - c0} contours vs {len(disc)}"
+        if closed:
+            assert len(p.entities) == n_ent[i], f"plane {i}: {n_ent[i]} entities vs {len(p.entities)}"
         for k, d in enumerate(disc):
             g = pts[int(ctpt[c0 + k]):int(ctpt[c0 + k + 1])]
             assert g.shape == d.shape, f"plane {i} contour {k}: {g.shape} vs {d.shape}"
@@ -82,7 +86,10 @@ def compare_sweep(vertices, faces, zs, interp_num, res=None, sweep=0, n_angles=0
         rep["contours"] += c1 - c0
         assert np.array_equal(bounds[i].reshape(2, 2), p.bounds), f"plane {i}: bounds"
         assert np.array_equal(cent[i], p.centroid), f"plane {i}: centroid"
-        good.append(i)
+        if closed:
+            good.append(i)
+        else:
+            assert n_ent[i] > c1 - c0, f"plane {i}: open chains not counted as entities"
     good = np.array(good, dtype=np.int64)
     if len(good) == P:          # the reference's array properties need every plane to have a section
         assert rel_err(area1, orc.areas1) < 1e-12

@@ -39,18 +39,35 @@ def test_cube_planes_through_faces_and_vertices(gpu_backend):
     assert (klass == oracle.trimesh_path.CLASS_VERTEX).any()
 
 
-def test_open_mesh_is_flagged_not_fatal(gpu_backend):
+def test_open_mesh_is_flagged_and_closed_contours_survive(gpu_backend):
+    """A sphere with a hole plus an intact sphere beside it: planes through the hole carry an open chain (flagged,
+    counted as an entity, no contour) AND the closed contour of the intact sphere, which must equal the oracle's."""
     v, f = meshio.icosphere(2, 10.0)
     keep = np.ones(len(f), dtype=bool)
     keep[np.argsort(v[f].mean(axis=1)[:, 0])[-40:]] = False          # cut a hole at +x
+    v2, f2 = meshio.icosphere(2, 7.0)
+    vv = np.vstack([v, v2 + np.array([-30.0, 1.0, 0.5])])
+    ff = np.vstack([f[keep], f2 + len(v)])
     zs = np.linspace(8.0, -8.0, 9)
-    res = run_gpu(v, f[keep], zs, 16)
-    status = res.array(_lib.ARR_STATUS)
-    orc = oracle.OracleSlices(v, f[keep], zs, 16, merge="topo")
+    rep = compare_sweep(vv, ff, zs, 16, expect_all_closed=False)
+    orc = rep["oracle"]
+    res = run_gpu(vv, ff, zs, 16)
+    status, n_ent = res.array(_lib.ARR_STATUS), res.array(_lib.ARR_N_ENT)
+    n_open_planes = 0
     for i, p in enumerate(orc.paths):
         closed = all(p.entity_closed(k) for k in range(len(p.entities)))
         assert bool(status[i] & _lib.ST_OPEN) == (not closed), i
-    assert (status & _lib.ST_OPEN).any() and not (status & _lib.ST_OPEN).all()
+        n_open_planes += not closed
+    assert 0 < n_open_planes < len(zs)
+    # every plane still has the closed contour of the intact sphere -> the array API works on all planes
+    from shoulder_b200.slice import GpuFullSlices
+
+    class Obb:
+        mesh = meshio.Mesh(vv, ff)
+    g = GpuFullSlices(Obb(), zslice_num=9, interp_num=16)
+    o = oracle.OracleSlices(vv, ff, g._zs, 16)
+    assert rel_err(g._ixy, o.ixy) < 1e-9
+    assert rel_err(g._areas1, np.array([max(q.area for q in p.polygons_closed) for p in o.paths])) < 1e-12
 
 
 def test_batch_of_bones_and_mixed_sweeps(gpu_backend, bone_obbs):
