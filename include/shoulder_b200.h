@@ -102,7 +102,8 @@ enum shb_array {
 #define SHB_ST_NONMANIFOLD  0x04u  /* a node has more than two incident segments                   */
 #define SHB_ST_RANK_TIE     0x08u  /* two distinct nodes share a rounded-coordinate hash (H4-i)    */
 #define SHB_ST_SPLIT_COPY   0x10u  /* two copies of one node round differently (H4-ii)             */
-#define SHB_ST_GENERAL      0x20u  /* plane was stitched by the general (serial DFS) path          */
+#define SHB_ST_GENERAL      0x20u  /* internal consistency check of the contour ranking failed; contours of the plane
+                                      are incomplete (never observed; kept as a guard instead of an out-of-bounds write) */
 
 typedef struct shb_batch  shb_batch;
 typedef struct shb_result shb_result;
