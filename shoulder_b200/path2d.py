@@ -141,10 +141,14 @@ class GpuPath2D:
         res, k = self._full() if self._full is not None else (self._res, self._k)
         off = res.array(_lib.ARR_SEG_OFF, k)
         s0, s1 = int(off[self._i]), int(off[self._i + 1])
-        to_3d = np.eye(4)
-        to_3d[2, 3] = self._z
-        return {
-            "face_index": np.array(res.array(_lib.ARR_FACE_INDEX, k)[s0:s1], dtype=np.int64),
-            "segments": np.array(res.array(_lib.ARR_SEGMENTS, k)[s0:s1]),
-            "to_3D": to_3d,
-        }
+        to_3d = getattr(self, "_to_3d", None)
+        if to_3d is None:
+            to_3d = np.eye(4)
+            to_3d[2, 3] = self._z
+        meta = {"to_3D": to_3d}
+        try:
+            meta["face_index"] = np.array(res.array(_lib.ARR_FACE_INDEX, k)[s0:s1], dtype=np.int64)
+            meta["segments"] = np.array(res.array(_lib.ARR_SEGMENTS, k)[s0:s1])
+        except _lib.BackendError:
+            pass                                   # the run did not keep mesh_multiplane's own outputs
+        return meta
