@@ -197,7 +197,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "planes_per_sec", "value": value, "unit": "planes/s", "n_gpus": args.gpus,
         "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps_ref, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_bones),
+        "config": workload_config(args, args.bones if args.workload != "cfg3" else 1),
         "bones_per_sec": n_bones * args.steps_ref / dt,
         "cpu_baseline": {"value": value, "unit": "planes/s", "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
