@@ -169,6 +169,10 @@ SHB_API int shb_result_totals(const shb_result* result, int64_t* n_plane, int64_
                       int64_t* n_contour, int64_t* n_point);
 SHB_API int shb_result_free(shb_result* result);
 
+/* The library caches device memory (stream-ordered pool, never trimmed on its own) and pinned host buffers between
+ * calls.  shb_trim() waits for outstanding work and hands everything that is idle back to the driver / OS. */
+SHB_API int shb_trim(void);
+
 /* Per-stage CUDA-event timing of shb_batch_run (adds one event pair per stage). */
 #define SHB_N_STAGES 7
 SHB_API int shb_profile_enable(int on);

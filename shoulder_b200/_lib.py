@@ -30,7 +30,7 @@ _DTYPES = {1: np.int32, 2: np.int64, 3: np.uint32, 4: np.float64, 5: np.float32}
 EXPORTS = (
     "shb_init", "shb_set_stream", "shb_batch_create", "shb_batch_free", "shb_batch_run", "shb_sweep_batch",
     "shb_result_fetch", "shb_result_fetch_async", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
-    "shb_profile_read", "shb_launch_count", "shb_last_error", "shb_abi_version",
+    "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
 )
 
 
@@ -108,6 +108,11 @@ def profile_read(reset: bool = True):
     n = (C.c_int64 * N_STAGES)()
     check(load().shb_profile_read(ms, n, 1 if reset else 0))
     return {STAGE_NAMES[i]: (ms[i], n[i]) for i in range(N_STAGES)}
+
+
+def trim() -> None:
+    """Give cached device memory and idle pinned buffers back (``shb_trim``)."""
+    check(load().shb_trim())
 
 
 def launch_count() -> int:

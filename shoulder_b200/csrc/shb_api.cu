@@ -59,6 +59,7 @@ struct Ctx {
     uint32_t* h_totals = nullptr;          // pinned readback slot
     unsigned long long* h_totals64 = nullptr;
     double2* angle_tab = nullptr; int angle_n = 0;
+    size_t pinned_limit = (size_t)16 << 30;   // bytes of pinned host cache kept across calls (SHB_PINNED_LIMIT_MB)
 } g;
 
 void* pinned_get(size_t bytes) {
@@ -67,6 +68,15 @@ void* pinned_get(size_t bytes) {
     for (auto& b : g.pinned)
         if (!b.used && b.size >= bytes && (!best || b.size < best->size)) best = &b;
     if (best && best->size <= 2 * bytes + (1 << 20)) { best->used = true; return best->p; }
+    // keep the cache bounded: beyond the limit, idle buffers are returned to the OS before a new one is pinned
+    size_t total = 0;
+    for (auto& b : g.pinned) total += b.size;
+    if (total + bytes > g.pinned_limit) {
+        for (size_t i = 0; i < g.pinned.size();) {
+            if (!g.pinned[i].used) { cudaFreeHost(g.pinned[i].p); g.pinned[i] = g.pinned.back(); g.pinned.pop_back(); }
+            else ++i;
+        }
+    }
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
     g.pinned.push_back({p, bytes, true});
@@ -184,6 +194,7 @@ SHB_API int shb_init(int device) {
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    if (const char* lim = getenv("SHB_PINNED_LIMIT_MB")) g.pinned_limit = (size_t)atoll(lim) << 20;
     CK(cudaHostAlloc(&g.h_totals, 8 * sizeof(uint32_t), cudaHostAllocMapped));       // written by k_publish, read after a stream sync
     CK(cudaHostAlloc(&g.h_totals64, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
     g.inited = true;
@@ -194,6 +205,21 @@ SHB_API int shb_set_stream(void* cuda_stream) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own;
+    return SHB_OK;
+}
+
+SHB_API int shb_trim(void) {
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    CK(cudaStreamSynchronize(g.stream));
+    CK(cudaStreamSynchronize(g.copy));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, g.device));
+    CK(cudaMemPoolTrimTo(pool, 0));
+    for (size_t i = 0; i < g.pinned.size();) {
+        if (!g.pinned[i].used) { cudaFreeHost(g.pinned[i].p); g.pinned[i] = g.pinned.back(); g.pinned.pop_back(); }
+        else ++i;
+    }
     return SHB_OK;
 }
 

@@ -276,3 +276,12 @@ def test_invalid_inputs_fail_loudly(gpu_backend):
     # the library is still usable afterwards
     res = _lib.sweep_batch([(v, f)], [(0, 0.0, np.linspace(-0.5, 0.5, 4), 8)], _lib.OUT_PLANE | _lib.OUT_IXY)
     assert (res.array(_lib.ARR_N_ENT) == 1).all()
+
+
+def test_trim_releases_caches_and_the_library_keeps_working(gpu_backend):
+    v, f = meshio.icosphere(3, 5.0)
+    zs = np.linspace(4.0, -4.0, 32)
+    a = run_gpu(v, f, zs, 64).array(_lib.ARR_IXY).copy()
+    _lib.trim()
+    b = run_gpu(v, f, zs, 64).array(_lib.ARR_IXY)
+    assert np.array_equal(a, b)
