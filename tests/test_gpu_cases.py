@@ -285,3 +285,19 @@ def test_trim_releases_caches_and_the_library_keeps_working(gpu_backend):
     _lib.trim()
     b = run_gpu(v, f, zs, 64).array(_lib.ARR_IXY)
     assert np.array_equal(a, b)
+
+
+def test_degenerate_batches(gpu_backend):
+    """planes that all miss, a mesh without faces, a sweep without planes beside a normal one"""
+    v, f = meshio.icosphere(2, 1.0)
+    res = _lib.sweep_batch([(v, f)], [(0, 0.0, np.array([5.0, 6.0, -7.0]), 8)], _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_CONTOURS)
+    assert (res.array(_lib.ARR_STATUS) == _lib.ST_EMPTY).all() and res.totals()["segments"] == 0
+    assert np.isnan(res.array(_lib.ARR_IXY)).all() and res.array(_lib.ARR_POINTS).shape == (0, 2)
+    empty = (np.zeros((0, 3)), np.zeros((0, 3), dtype=np.int64))
+    res = _lib.sweep_batch([empty, (v, f)], [(0, 0.0, np.array([0.0, 0.1]), 8), (1, 0.0, np.zeros(0), 8), (1, 0.0, np.array([0.0, 0.3]), 16)],
+                           _lib.OUT_PLANE | _lib.OUT_IXY)
+    assert (res.array(_lib.ARR_STATUS, 0) == _lib.ST_EMPTY).all()
+    assert res.array(_lib.ARR_N_ENT, 1).shape == (0,)
+    assert (res.array(_lib.ARR_N_ENT, 2) == 1).all() and res.array(_lib.ARR_IXY, 2).shape == (2, 2, 16)
+    res = _lib.sweep_batch([empty], [(0, 0.0, np.array([0.0]), 4)], _lib.OUT_PLANE)      # nothing to slice at all
+    assert res.array(_lib.ARR_N_SEG)[0] == 0
