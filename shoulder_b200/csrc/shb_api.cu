@@ -455,6 +455,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     const uint32_t S = g.h_totals[SHB_T_S], maxcand = g.h_totals[SHB_T_MAXN];
     if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
     r->W = S; r->S = S;
+    const uint32_t avgn = (uint32_t)(S / std::max<uint32_t>(G, 1u));     // mean segments per plane picks the CTA size
     CK(dalloc(&d.hits, (size_t)S + 8, st));      // + slack: TMA copies are widened to 16-byte boundaries
     CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
     CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
@@ -485,8 +486,8 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     }
 
     { StageTimer t(3); t.stop(shb_launch_intersect(d, 1, st)); }
-    { StageTimer t(5); t.stop(shb_launch_stitch(d, maxcand, g.n_sm, st)); }
-    if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, b->max_interp, g.n_sm, st)); }
+    { StageTimer t(5); t.stop(shb_launch_stitch(d, maxcand, avgn, g.n_sm, st)); }
+    if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);

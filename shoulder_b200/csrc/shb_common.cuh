@@ -127,8 +127,8 @@ int shb_launch_scan_planes(const ShbDev& d, cudaStream_t st);
 int shb_launch_scatter(const ShbDev& d, cudaStream_t st);
 int shb_launch_intersect(const ShbDev& d, int fill, cudaStream_t st);
 int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
-int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, int n_sm, cudaStream_t st);
-int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t maxN, int n_sm, cudaStream_t st);
+int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, int n_sm, cudaStream_t st);
+int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t maxN, int n_sm, cudaStream_t st);
 int shb_launch_compact(const ShbDev& d, const uint32_t* ct_off, const uint32_t* pt_off,
                        double* pts_out, int64_t* ctpt_out, double* ctarea_out, cudaStream_t st);
 int shb_launch_scan_contours(const ShbDev& d, uint32_t* ct_off, uint32_t* pt_off, cudaStream_t st);
