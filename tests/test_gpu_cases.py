@@ -301,3 +301,22 @@ def test_degenerate_batches(gpu_backend):
     assert (res.array(_lib.ARR_N_ENT, 2) == 1).all() and res.array(_lib.ARR_IXY, 2).shape == (2, 2, 16)
     res = _lib.sweep_batch([empty], [(0, 0.0, np.array([0.0]), 4)], _lib.OUT_PLANE)      # nothing to slice at all
     assert res.array(_lib.ARR_N_SEG)[0] == 0
+
+
+def test_h4_coordinate_hash_vs_topological_merge_is_reported_not_hidden(gpu_backend):
+    """two distinct crossing points closer than 1e-8 hash equal in trimesh (they fuse into a degree-4
+    node), while the GPU merges on the mesh edge and keeps two contours.  The oracle reports such planes
+    (info['agree'] == False); the comparison lists them instead of asserting connectivity on them."""
+    v0 = np.array([[x, y, z] for x in (0.0, 1.0) for y in (0.0, 1.0) for z in (0.0, 1.0)])
+    f0 = np.array([[0, 2, 3], [0, 3, 1], [4, 5, 7], [4, 7, 6], [0, 1, 5], [0, 5, 4], [2, 6, 7], [2, 7, 3],
+                   [0, 4, 6], [0, 6, 2], [1, 3, 7], [1, 7, 5]])
+    v = np.vstack([v0, v0 + np.array([1.0 + 2e-9, 0.0, 0.0])])        # second cube 2e-9 to the right of the first
+    f = np.vstack([f0, f0 + len(v0)])
+    zs = np.array([0.25, 0.5, 0.75])
+    rep = compare_sweep(v, f, zs, 16, expect_all_closed=False)
+    assert rep["h4_exceptions"] == [0, 1, 2]
+    res = run_gpu(v, f, zs, 16)
+    assert (res.array(_lib.ARR_N_ENT) == 2).all()                      # two unit squares, not one fused figure
+    areas = res.array(_lib.ARR_CONTOUR_AREA)
+    assert np.allclose(areas, 1.0, rtol=1e-12)
+    assert (res.array(_lib.ARR_STATUS) & (_lib.ST_OPEN | _lib.ST_NONMANIFOLD) == 0).all()
