@@ -441,6 +441,8 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
         if (v >= 1) { d.stitch_cap = std::min(d.stitch_cap, v); d.resample_cap = std::min(d.resample_cap, v + 2); }
     }
     cap = d.stitch_cap; pcap = d.resample_cap;
+    d.debug = 0;
+    if (const char* f = getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= atoi(f) ? 1u : 0u;      // test hook
     { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
     { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
     { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }

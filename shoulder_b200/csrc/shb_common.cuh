@@ -34,6 +34,13 @@ struct ShbPlaneMeta {
     uint32_t sel_len;     // its point count including the closing duplicate
     uint32_t n_pts;       // points written for the plane (closing duplicates included)
     uint32_t n_open;      // open chains: entities without a contour; len(Path2D.entities) = n_ent + n_open
+    // what the resample kernel needs of the plane's sweep, so that it starts from ONE record instead of the
+    // plane -> sorted plane -> sweep -> descriptor chain of dependent loads
+    uint32_t interp_num;  // N of the plane's sweep
+    uint32_t pad;
+    uint64_t prof_row;    // element offset of the plane's (2, N) block in every profile array
+    uint64_t rad_row;     // element offset of the plane's A rays in the radius image
+    uint64_t sel_pt;      // index (in points) of the outline's first point in ShbDev::pts
 };
 
 struct ShbDev {
@@ -87,6 +94,7 @@ struct ShbDev {
     uint32_t  outputs_mask;
     uint32_t  stitch_cap;        // largest n handled in shared memory
     uint32_t  resample_cap;      // largest point count handled in shared memory
+    uint32_t  debug;             // test hooks: bit 0 = radius image by the all-candidates path on every plane
 };
 
 enum { SHB_T_M = 0, SHB_T_W = 1, SHB_T_MAXCAND = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
@@ -111,8 +119,13 @@ __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
     return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + n /*lone-vertex signs*/ + 96 +
            8 * E /*start-node coordinates of the fast path*/;
 }
+// outline (16 B) + chord lengths / vertex angles (8 B) per point; region X = per-edge slopes, later theta / r;
+// region Y = resampled x / y, later the ray accumulators (8 B) + ray owners (4 B); sort keys only when a theta-sorted array is requested
+__host__ __device__ inline size_t shb_resample_x_bytes(uint32_t npts, uint32_t N) { return 16 * (size_t)(npts > N ? npts : N); }
+__host__ __device__ inline size_t shb_resample_y_bytes(uint32_t N, uint32_t A) { return 16 * (size_t)N > 12 * (size_t)A ? 16 * (size_t)N : 12 * (size_t)A; }
 __host__ __device__ inline size_t shb_resample_ws_bytes(uint32_t npts, uint32_t N, uint32_t A, bool sorted = true) {
-    return 24 * ((size_t)npts + 1) + 32 * (size_t)N + (sorted ? 12 * (size_t)shb_pow2_ge(N) : 0) + 8 * (size_t)A + 64;
+    return 24 * ((size_t)npts + 1) + 16 + shb_resample_x_bytes(npts, N) + shb_resample_y_bytes(N, A) +
+           (sorted ? 12 * (size_t)shb_pow2_ge(N) : 0) + 64;
 }
 
 #ifdef __cplusplus

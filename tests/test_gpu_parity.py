@@ -21,7 +21,7 @@ def test_ellipsoid(gpu_backend):
 
 def test_torus_two_loops(gpu_backend):
     v, f = meshio.torus(30.0, 8.0, 64, 32)
-    rep = compare_sweep(v, f, _zs(v, 40, 0.97), 128)
+    rep = compare_sweep(v, f, _zs(v, 40, 0.97), 128, n_angles=90)      # centroid outside the outline: all-candidates rays
     assert rep["contours"] > 40            # planes through the hole cut two loops
 
 
@@ -66,3 +66,23 @@ def test_fast_mode_matches_full_mode(gpu_backend, bone_obbs):
     assert np.allclose(fast.array(_lib.ARR_AREA1), full.array(_lib.ARR_AREA1), rtol=1e-13)
     with pytest.raises(_lib.BackendError):
         fast.array(_lib.ARR_SEGMENTS)
+
+
+def test_radial_ray_parallel_path_equals_the_all_candidates_path(gpu_backend, bone_obbs):
+    """Star-shaped outlines take a ray-parallel path (one owner edge per ray); it must deliver the bits of the
+    edge-parallel all-candidates path that every other outline takes."""
+    import os
+    from shoulder_b200 import _lib
+    from helpers import run_gpu
+    m = bone_obbs("humerus_left").mesh
+    zs = np.linspace(0.99 * m.vertices[:, 2].max(), 0.99 * m.vertices[:, 2].min(), 400)
+    mask = _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_RADIAL
+    fast = run_gpu(m.vertices, m.faces, zs, 64, mask, 360).array(_lib.ARR_RADIAL)
+    os.environ["SHB_DEBUG_RADIAL_GENERAL"] = "1"
+    try:
+        slow = run_gpu(m.vertices, m.faces, zs, 64, mask, 360).array(_lib.ARR_RADIAL)
+        slow7 = run_gpu(m.vertices, m.faces, zs, 64, mask, 7).array(_lib.ARR_RADIAL)
+    finally:
+        del os.environ["SHB_DEBUG_RADIAL_GENERAL"]
+    assert np.array_equal(fast, slow) and np.isfinite(fast).all() and (fast > 0).mean() > 0.9     # 0 = ray misses the outline
+    assert np.array_equal(run_gpu(m.vertices, m.faces, zs, 64, mask, 7).array(_lib.ARR_RADIAL), slow7)     # few, wide rays
