@@ -133,7 +133,7 @@ struct shb_batch {
     std::vector<ShbSweep> sweeps;          // host copy
     double4* vert = nullptr; double* vz = nullptr; int4* face = nullptr;
     ShbSweep* d_sweep = nullptr; uint32_t* d_item_off = nullptr;
-    double* h_sorted = nullptr; double* h_orig = nullptr;
+    double* h_sorted = nullptr; double* h_orig = nullptr; double* oz = nullptr;
     uint32_t *plane_out = nullptr, *plane_in = nullptr, *plane_sweep = nullptr;
     uint32_t* d_bad = nullptr;             // set by K0 when a face names a vertex outside its mesh; checked at the first run
     Staging* stage = nullptr;              // pinned copies of the library-built arrays, held until the upload has executed
@@ -252,7 +252,7 @@ SHB_API int shb_batch_free(shb_batch* b) {
     if (b->stage) { cudaStreamSynchronize(st); delete b->stage; b->stage = nullptr; }
     dfree(b->d_bad, st);
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
-    dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st);
+    dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->oz, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st);
     delete b;
     return SHB_OK;
 }
@@ -271,7 +271,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     for (int m = 0; m < n_mesh; ++m)
         if (vert_off[m + 1] < vert_off[m] || face_off[m + 1] < face_off[m]) return fail(SHB_E_INVALID, "offsets of mesh %d decrease", m);
     const int64_t nv = vert_off[n_mesh], nf = face_off[n_mesh], G64 = height_off[n_sweep];
-    if (nv >= (int64_t)1 << 31 || nf >= (int64_t)1 << 30) return fail(SHB_E_CAPACITY, "too many vertices/faces in one batch");
+    if (nv >= (int64_t)1 << 31 || nf >= (int64_t)1 << 29) return fail(SHB_E_CAPACITY, "too many vertices/faces in one batch");
     if (G64 <= 0 || G64 >= (int64_t)1 << 31) return fail(SHB_E_CAPACITY, "plane count %lld out of range", (long long)G64);
 
     struct BatchDel { void operator()(shb_batch* p) const { shb_batch_free(p); } };
@@ -279,7 +279,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     b->n_mesh = n_mesh; b->n_sweep = n_sweep; b->n_vert = nv; b->n_face = nf; b->G = (uint32_t)G64;
     b->sweeps.resize(n_sweep);
     std::vector<uint32_t> item_off(n_sweep + 1, 0);
-    std::vector<double> hs(G64), ho(heights, heights + G64);
+    std::vector<double> hs(G64), ho(heights, heights + G64), oz(G64);
     std::vector<uint32_t> pout(G64), pin(G64), psw(G64);
     uint64_t prof = 0, items = 0;
     std::vector<uint32_t> idx;
@@ -309,6 +309,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
             std::iota(idx.begin(), idx.end(), 0u);
             std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t c) { return h[a] < h[c]; });
         }
+        for (int64_t i = 0; i < P; ++i) oz[p0 + i] = z_orig[s] + h[i];        // one rounding, like numpy's origin + normal * height
         for (int64_t i = 0; i < P; ++i) {
             if (!(h[idx[i]] == h[idx[i]])) return fail(SHB_E_INVALID, "NaN height in sweep %d", s);
             hs[p0 + i] = h[idx[i]];
@@ -330,7 +331,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     CK(dalloc(&d_voff, n_mesh + 1, st)); CK(dalloc(&d_foff, n_mesh + 1, st)); CK(dalloc(&b->d_bad, 1, st));
     CK(dalloc(&b->vert, nv, st)); CK(dalloc(&b->vz, nv, st)); CK(dalloc(&b->face, nf, st));
     CK(dalloc(&b->d_sweep, n_sweep, st)); CK(dalloc(&b->d_item_off, n_sweep + 1, st));
-    CK(dalloc(&b->h_sorted, G64, st)); CK(dalloc(&b->h_orig, G64, st));
+    CK(dalloc(&b->h_sorted, G64, st)); CK(dalloc(&b->h_orig, G64, st)); CK(dalloc(&b->oz, G64, st));
     CK(dalloc(&b->plane_out, G64, st)); CK(dalloc(&b->plane_in, G64, st)); CK(dalloc(&b->plane_sweep, G64, st));
     double T1 = now();
     CK(cudaMemcpyAsync(raw_v, verts, 3 * (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -344,6 +345,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     CK(stage.copy(b->d_item_off, item_off.data(), (n_sweep + 1) * sizeof(uint32_t), st));
     CK(stage.copy(b->h_sorted, hs.data(), G64 * sizeof(double), st));
     CK(stage.copy(b->h_orig, ho.data(), G64 * sizeof(double), st));
+    CK(stage.copy(b->oz, oz.data(), G64 * sizeof(double), st));
     CK(stage.copy(b->plane_out, pout.data(), G64 * sizeof(uint32_t), st));
     CK(stage.copy(b->plane_in, pin.data(), G64 * sizeof(uint32_t), st));
     CK(stage.copy(b->plane_sweep, psw.data(), G64 * sizeof(uint32_t), st));
@@ -404,7 +406,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     r->rad_total = rad;
     ShbDev& d = r->d;
     d.vert = b->vert; d.vz = b->vz; d.face = b->face; d.item_off = b->d_item_off;
-    d.h_sorted = b->h_sorted; d.h_orig = b->h_orig; d.plane_out = b->plane_out; d.plane_in = b->plane_in; d.plane_sweep = b->plane_sweep;
+    d.h_sorted = b->h_sorted; d.h_orig = b->h_orig; d.oz = b->oz; d.plane_out = b->plane_out; d.plane_in = b->plane_in; d.plane_sweep = b->plane_sweep;
     d.n_sweep = (uint32_t)b->n_sweep; d.n_plane = G; d.n_item = b->n_item;
     d.n_angles = (uint32_t)n_angles; d.outputs_mask = outputs_mask;
     // sweep descriptors carry the radial offsets of this run
@@ -458,7 +460,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
     r->W = S; r->S = S;
     const uint32_t avgn = (uint32_t)(S / std::max<uint32_t>(G, 1u));     // mean segments per plane picks the CTA size
-    CK(dalloc(&d.hits, (size_t)S + 8, st));      // + slack: TMA copies are widened to 16-byte boundaries
+    CK(dalloc(&d.hits, (size_t)S + 1, st));      // 16-byte records: every plane's list is a TMA-aligned run
     CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
     CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
     const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define SHB_TOL_MERGE 1e-8     // trimesh.constants.tol.merge  (sign classification band)
+#define SHB_HIT_FACE   0x1FFFFFFFu   // face bits of a hit record's x word
 
 // sweep descriptor, one per (mesh, height list) pair — device resident
 struct ShbSweep {
@@ -52,6 +53,7 @@ struct ShbDev {
     const uint32_t* item_off;    // [n_sweep+1] prefix of faces per sweep
     const double*   h_sorted;    // [G] heights ascending within each sweep
     const double*   h_orig;      // [G] heights in caller order (indexed by original plane)
+    const double*   oz;          // [G] plane z = fl(z_orig + height), caller order (trimesh: new_origin = origin + normal * height)
     const uint32_t* plane_out;   // [G] sorted plane -> original global plane
     const uint32_t* plane_in;    // [G] original global plane -> sorted plane
     const uint32_t* plane_sweep; // [G] sweep of sorted plane
@@ -66,7 +68,9 @@ struct ShbDev {
     uint32_t* tile_sum;   // [ceil(G/4096)] scan scratch
     uint32_t* totals;     // [8]   M, -, -, S, maxn, nbig, ...
     uint4*    rec;        // [n_item] bucketed triangles (face, lo, span, sweep); first M are live
-    uint32_t* hits;       // [S]   per-plane lists of global face ids, caller plane order
+    uint4*    hits;       // [S]   per-plane hit records, caller plane order: x = global face id | tag << 29 | (lone vertex above) << 31,
+                          //       y, z, w = lone vertex u and the two others in cyclic order (basic crossings, tag = position of u);
+                          //       tag 3 = a vertex on the plane (the stitcher classifies such faces itself)
     uint32_t* seg_off;    // [G+1] exact segment offsets, original plane order
     uint32_t* big_list;   // [G]   planes too large for shared memory
     // ---- outputs (device)
@@ -111,13 +115,23 @@ __host__ __device__ inline uint32_t shb_pow2_ge(uint32_t x) {
 #endif
 }
 __host__ __device__ inline uint32_t shb_hash_size(uint32_t n) { return shb_pow2_ge(2 * n + n / 2 + 1); }
+// fast path of the stitcher: mate[E] | node keys[E] (later rank keys + next/prev) | hash table (later jump pairs) |
+// staged hit records[n] | start-node coordinates[n]
+__host__ __device__ inline size_t shb_stitch_fast_table_bytes(uint32_t n) {
+    size_t t = 4 * (size_t)shb_hash_size(n), p = 8 * (size_t)n;
+    return ((t > p ? t : p) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t shb_stitch_fast_bytes(uint32_t n) {
+    return 8 * (size_t)n + 16 * (size_t)n + shb_stitch_fast_table_bytes(n) + 16 * (size_t)n + 16 * (size_t)n + 16;
+}
 __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
     size_t E = 2 * (size_t)n;
     size_t c1 = 4 * (size_t)shb_pow2_ge(n) + 4 * (size_t)shb_hash_size(n);   // sort keys + hash table
     size_t c2 = 12 * E;                                                       // jump pairs + heads
     size_t c = c1 > c2 ? c1 : c2;
-    return 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + n /*lone-vertex signs*/ + 96 +
-           8 * E /*start-node coordinates of the fast path*/;
+    size_t g = 4 * E /*mate*/ + 8 * E /*node key | rank key | area acc*/ + c + 4 * E /*contour list + starts*/ + n /*lone-vertex signs*/ + 96;
+    size_t f = shb_stitch_fast_bytes(n);
+    return g > f ? g : f;
 }
 // outline (16 B) + chord lengths / vertex angles (8 B) per point; region X = per-edge slopes, later theta / r;
 // region Y = resampled x / y, later the ray accumulators (8 B) + ray owners (4 B); sort keys only when a theta-sorted array is requested
