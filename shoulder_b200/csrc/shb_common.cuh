@@ -141,6 +141,21 @@ __host__ __device__ inline size_t shb_resample_ws_bytes(uint32_t npts, uint32_t 
     return 24 * ((size_t)npts + 1) + 16 + shb_resample_x_bytes(npts, N) + shb_resample_y_bytes(N, A) +
            (sorted ? 12 * (size_t)shb_pow2_ge(N) : 0) + 64;
 }
+// byte offsets of the resample workspace's arrays, fixed per LAUNCH (capacity npts points, N samples, A rays): they
+// reach the kernel as parameters, so no thread derives an address from its plane's own point count
+struct ShbRsLayout { uint32_t dd, x, rr, y, sy, own, skeys, svals; };
+inline ShbRsLayout shb_resample_layout(uint32_t npts, uint32_t N, uint32_t A) {
+    ShbRsLayout L;
+    L.dd = 16u * (npts + 1);
+    L.x = (24u * (npts + 1) + 15u) & ~15u;
+    L.rr = L.x + 8u * N;
+    L.y = L.x + (uint32_t)shb_resample_x_bytes(npts, N);
+    L.sy = L.y + 8u * N;
+    L.own = L.y + 8u * A;
+    L.skeys = L.y + (uint32_t)shb_resample_y_bytes(N, A);
+    L.svals = L.skeys + 8u * shb_pow2_ge(N);
+    return L;
+}
 
 #ifdef __cplusplus
 extern "C" {
