@@ -48,6 +48,7 @@ struct Ctx {
     size_t smem_optin = 0;
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t copy = nullptr;           // device->host copies run here so they overlap the next batch's kernels
+    cudaEvent_t sized = nullptr;           // recorded behind the size publication of a run
     int64_t launches = 0;
     bool profile = false;
     double stage_ms[SHB_N_STAGES] = {};
@@ -190,6 +191,7 @@ SHB_API int shb_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
     g.stream = g.own;
     CK(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.sized, cudaEventDisableTiming));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;
@@ -367,7 +369,7 @@ SHB_API int shb_result_free(shb_result* r) {
     cudaStream_t st = g.stream;
     ShbDev& d = r->d;
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
-    dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.totals, st); dfree(d.totals64, st);
+    dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.totals, st); dfree(d.totals64, st);
     dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
     dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
     dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
@@ -418,15 +420,15 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
 
     CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
     CK(dalloc(&d.inc, G, st)); CK(dalloc(&d.sort_off, G + 1, st)); CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cnt, G, st));
-    CK(dalloc(&d.tile_sum, (G + 4095) / 4096 + 1, st));
+    CK(dalloc(&d.tile_sum, (G + 4095) / 4096 + 1, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st));
     CK(dalloc(&d.totals, 8, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
     CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
     CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
     CK(dalloc(&d.o_sel, 2 * (size_t)G, st));
     CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.cnt, 0, G * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, ((size_t)G + 1) * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.totals, 0, 8 * sizeof(uint32_t), st));
-    CK(cudaMemcpyAsync(d.totals + SHB_T_W, b->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));   // slot 1: bad-face flag
+    CK(cudaMemcpyAsync(d.totals + SHB_T_BAD, b->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));   // slot 1: bad-face flag
 
     // shared-memory capacities (leave headroom for static shared memory)
     const size_t budget = (g.smem_optin > 8192 ? g.smem_optin - 4096 : 40960);
@@ -445,20 +447,23 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     cap = d.stitch_cap; pcap = d.resample_cap;
     d.debug = 0;
     if (const char* f = getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= atoi(f) ? 1u : 0u;      // test hook
+    // K1 sizes everything downstream: the candidate triangles per plane (an upper bound of the hits that is exact
+    // except on planes through vertices) are published as soon as the bucket histograms are scanned, and the host
+    // waits for them while the device goes on with the counting sort
     { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
+    { StageTimer t(1); t.stop(shb_launch_scan_candidates(d, st)); }
+    g.launches += shb_launch_publish(d.totals, 8, d.totals64, g.h_totals, g.h_totals64, st);
+    CK(cudaEventRecord(g.sized, st));
     { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
     { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st));      // reused as the hit-list cursors
-    { StageTimer t(3); t.stop(shb_launch_intersect(d, 0, st)); }
-    { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
-    g.launches += shb_launch_publish(d.totals, 8, d.totals64, g.h_totals, g.h_totals64, st);
-    CK(cudaStreamSynchronize(st));          // the one mid-pipeline sync: sizes of everything downstream
+    CK(cudaEventSynchronize(g.sized));      // the one host wait of a run
     stage.release();
     if (b->stage) { delete b->stage; b->stage = nullptr; }      // the batch upload has executed too
-    if (g.h_totals[SHB_T_W]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
-    const uint32_t S = g.h_totals[SHB_T_S], maxcand = g.h_totals[SHB_T_MAXN];
-    if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu segments in one batch; split it", g.h_totals64[0]);
-    r->W = S; r->S = S;
+    if (g.h_totals[SHB_T_BAD]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
+    const uint32_t S = g.h_totals[SHB_T_CAP], maxcand = g.h_totals[SHB_T_MAXN];      // S: capacity (candidates), >= segments
+    if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu candidate segments in one batch; split it", g.h_totals64[0]);
+    r->W = S;
     const uint32_t avgn = (uint32_t)(S / std::max<uint32_t>(G, 1u));     // mean segments per plane picks the CTA size
     CK(dalloc(&d.hits, (size_t)S + 1, st));      // 16-byte records: every plane's list is a TMA-aligned run
     CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
@@ -489,14 +494,15 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
         CK(dalloc(&d.scratch, d.scratch_stride * (size_t)g.n_sm, st));
     }
 
-    { StageTimer t(3); t.stop(shb_launch_intersect(d, 1, st)); }
+    { StageTimer t(3); t.stop(shb_launch_intersect(d, st)); }
+    { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
     { StageTimer t(5); t.stop(shb_launch_stitch(d, maxcand, avgn, g.n_sm, st)); }
     if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
     dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st);
-    dfree(d.cnt, st); dfree(d.scratch, st);
+    dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.scratch, st);
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
     CK(cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming));
     CK(cudaEventRecord(r->done, st));
@@ -557,7 +563,7 @@ static int enqueue_fetch(shb_result* r, uint32_t mask) {
     bool sync = false;
     if ((mask & SHB_OUT_SEGMENTS) && !r->have_seg) {
         if (!(r->mask & SHB_OUT_SEGMENTS)) return fail(SHB_E_STATE, "segments / face_index were not in the outputs_mask of the run");
-        const size_t S = r->S;
+        const size_t S = r->W;                  // capacity: the exact count is seg_off[G], known once the plane arrays are in
         r->h_face_index = (int32_t*)pinned_get(S * 4); r->h_segments = (double*)pinned_get(S * 32);
         if (!r->h_face_index || !r->h_segments) return fail(SHB_E_NOMEM, "pinned host allocation failed");
         CK(cudaMemcpyAsync(r->h_face_index, r->d.face_index, S * 4, cudaMemcpyDeviceToHost, st));
@@ -620,7 +626,7 @@ SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n
     if (rc) return rc;
     if ((rc = finish_fetch(r))) return rc;
     if (n_plane) *n_plane = r->G;
-    if (n_seg) *n_seg = r->S;
+    if (n_seg) *n_seg = r->h_seg_off[r->G];
     if (n_contour || n_point) {
         int64_t c = 0, p = 0;
         if (r->have_cont) { c = r->n_cont; p = r->n_pts; }

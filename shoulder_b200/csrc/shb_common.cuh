@@ -63,8 +63,10 @@ struct ShbDev {
     uint32_t* item_span;  // [n_item]
     uint32_t* inc;        // [G]   #triangles whose range starts at (sorted) plane = counting-sort histogram
     uint32_t* sort_off;   // [G+1] bucket offsets
-    uint32_t* sort_cur;   // [G]   bucket cursors (scatter), then hit-list cursors (intersect fill)
-    uint32_t* cnt;        // [G]   exact hits per sorted plane
+    uint32_t* sort_cur;   // [G]   bucket cursors (scatter), then hit-list cursors (intersect) = exact hits per sorted plane
+    uint32_t* dec;        // [G+1] #triangles whose range ends before (sorted) plane
+    uint32_t* cnt;        // [G]   candidate triangles per sorted plane (ranges covering it) >= exact hits
+    uint32_t* cap_off;    // [G+1] hit-list offsets by candidate capacity, original plane order
     uint32_t* tile_sum;   // [ceil(G/4096)] scan scratch
     uint32_t* totals;     // [8]   M, -, -, S, maxn, nbig, ...
     uint4*    rec;        // [n_item] bucketed triangles (face, lo, span, sweep); first M are live
@@ -101,7 +103,7 @@ struct ShbDev {
     uint32_t  debug;             // test hooks: bit 0 = radius image by the all-candidates path on every plane
 };
 
-enum { SHB_T_M = 0, SHB_T_W = 1, SHB_T_MAXCAND = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
+enum { SHB_T_M = 0, SHB_T_BAD = 1, SHB_T_CAP = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
        SHB_T_NCONT = 6, SHB_T_NPTS = 7 };
 
 // bytes of workspace the stitch kernel needs for a plane with n segments
@@ -167,7 +169,8 @@ int shb_launch_prep_mesh(const double* verts_in, const int64_t* faces_in, const 
 int shb_launch_bucket(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_planes(const ShbDev& d, cudaStream_t st);
 int shb_launch_scatter(const ShbDev& d, cudaStream_t st);
-int shb_launch_intersect(const ShbDev& d, int fill, cudaStream_t st);
+int shb_launch_intersect(const ShbDev& d, cudaStream_t st);
+int shb_launch_scan_candidates(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
 int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, int n_sm, cudaStream_t st);
 int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t maxN, int n_sm, cudaStream_t st);
