@@ -160,10 +160,10 @@ def stage_alg_bytes(stage: str, c: dict) -> float:
         return 16 * T + 8 * V + 8 * P + 8 * items
     if stage == "scatter":
         return 8 * items + 16 * c["M"]
-    if stage == "intersect":
-        return 16 * c["M"] + 16 * T + 8 * V + 8 * P + 4 * S
-    if stage == "stitch":       # hit list + mesh once in; closed contours + plane records out (+ face_index, segments when requested)
-        return 4 * S + 16 * T + 32 * V + (36 * S if c.get("full") else 0) + 16 * (S + C) + 20 * C + 164 * P
+    if stage == "intersect":    # bucketed triangles + mesh z in; 16-byte hit records out (one pass)
+        return 16 * c["M"] + 16 * T + 8 * V + 8 * P + 16 * S
+    if stage == "stitch":       # hit records + mesh once in; closed contours + plane records out (+ face_index, segments when requested)
+        return 16 * S + 16 * T + 32 * V + (36 * S if c.get("full") else 0) + 16 * (S + C) + 20 * C + 200 * P
     if stage == "resample":     # chosen outlines in; k profile arrays + radius image out
         return 16 * (S + C) + 8 * c["k"] * 2 * PN + 8 * A + 88 * P
     return 8 * P * 6
@@ -362,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
     # whole step: inputs once + the outputs this run delivers (intermediates such as hit lists and contour points are not credited)
     pipeline_alg = 24 * V + 12 * T + 8 * k_prof * 2 * PN + 8 * PA + 76 * P
     traffic = None
-    tfile = ROOT / "profiles" / "r1e_traffic.json"
+    tfile = ROOT / "profiles" / "r1g_traffic.json"
     if tfile.exists() and args.workload == "cfg2" and bones == 32 and args.planes == 2048 and args.interp == 360 and args.angles == 360:
         for name, rec in json.loads(tfile.read_text())["kernels"].items():     # ncu --set full capture of this very command
             if name.startswith("k_" + dom) and not name.endswith("<0>"):

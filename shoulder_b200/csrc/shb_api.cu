@@ -457,7 +457,11 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
     { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st));      // reused as the hit-list cursors
+    const bool dbg_t = getenv("SHB_DEBUG_TIMING") != nullptr;
+    auto now_ms = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    const double tw0 = now_ms();
     CK(cudaEventSynchronize(g.sized));      // the one host wait of a run
+    const double tw1 = now_ms();
     stage.release();
     if (b->stage) { delete b->stage; b->stage = nullptr; }      // the batch upload has executed too
     if (g.h_totals[SHB_T_BAD]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
@@ -506,6 +510,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
     CK(cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming));
     CK(cudaEventRecord(r->done, st));
+    if (dbg_t) fprintf(stderr, "[shb] run: host waited %.3f ms for the sizes, then enqueued the rest in %.3f ms\n", tw1 - tw0, now_ms() - tw1);
     *out = r.release();
     return SHB_OK;
 }
