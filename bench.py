@@ -229,6 +229,7 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line, nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     _lib.init(local_rank)
     # an explicit (non-NULL) stream: the library enqueues on it and the torch events below are recorded on it
