@@ -117,14 +117,14 @@ __host__ __device__ inline uint32_t shb_pow2_ge(uint32_t x) {
 #endif
 }
 __host__ __device__ inline uint32_t shb_hash_size(uint32_t n) { return shb_pow2_ge(2 * n + n / 2 + 1); }
-// fast path of the stitcher: mate[E] | node keys[E] (later rank keys + next/prev) | hash table (later jump pairs) |
-// staged hit records[n] | start-node coordinates[n]
+// fast path of the stitcher: staged hit records, later the start-node coordinates [n x 16 B] | node keys [E x 8] |
+// mate [E x 4] | record head words [n x 4] | hash table, later next / prev / jump words [max(4H, 12n)]
 __host__ __device__ inline size_t shb_stitch_fast_table_bytes(uint32_t n) {
-    size_t t = 4 * (size_t)shb_hash_size(n), p = 8 * (size_t)n;
+    size_t t = 4 * (size_t)shb_hash_size(n), p = 12 * (size_t)n;
     return ((t > p ? t : p) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t shb_stitch_fast_bytes(uint32_t n) {
-    return 8 * (size_t)n + 16 * (size_t)n + shb_stitch_fast_table_bytes(n) + 16 * (size_t)n + 16 * (size_t)n + 16;
+    return 16 * (size_t)n + 16 * (size_t)n + 8 * (size_t)n + 4 * (size_t)n + shb_stitch_fast_table_bytes(n) + 16;
 }
 __host__ __device__ inline size_t shb_stitch_ws_bytes(uint32_t n) {
     size_t E = 2 * (size_t)n;
