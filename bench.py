@@ -229,8 +229,19 @@ def run_ours(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the ONE JSON line, nothing else
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # stdout carries the ONE JSON line and nothing else: NCCL prints its version banner there when the first
+        # communicator comes up, so fd 1 points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _lib.init(local_rank)
     # an explicit (non-NULL) stream: the library enqueues on it and the torch events below are recorded on it
     stream = torch.cuda.Stream()
