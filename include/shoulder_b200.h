@@ -122,6 +122,8 @@ SHB_API int shb_set_stream(void* cuda_stream);
  *   and resamples each outline to interp_num[k] points.
  * The upload is only enqueued: verts / faces must stay valid until the first shb_batch_run on the batch returns
  * (or the batch is freed); an out-of-range face index is reported by that run (SHB_E_INVALID).
+ * Limits per batch (SHB_E_CAPACITY beyond them; split the batch): < 2^31 vertices, < 2^29 faces, < 2^31 planes,
+ * < 2^32 (sweep, face) pairs, < 2^31 candidate segments (reported by the run).
  * Replaces the argument set of slice.py:24-28 plus Slices.__init__ (slice.py:10-19). */
 SHB_API int shb_batch_create(int32_t n_mesh,
                      const double* verts, const int64_t* vert_off,
