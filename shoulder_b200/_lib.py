@@ -99,8 +99,15 @@ def set_stream(stream_ptr: int | None) -> None:
     check(load().shb_set_stream(C.c_void_p(stream_ptr or 0)))
 
 
-def profile_enable(on: bool) -> None:
-    check(load().shb_profile_enable(1 if on else 0))
+def profile_enable(on, stages=None) -> None:
+    """on: bool.  stages: optional iterable of stage names (STAGE_NAMES) to time; default every stage."""
+    if not on:
+        code = 0
+    elif stages is None:
+        code = 1
+    else:
+        code = sum(2 << STAGE_NAMES.index(s) for s in stages)
+    check(load().shb_profile_enable(code))
 
 
 def profile_read(reset: bool = True):

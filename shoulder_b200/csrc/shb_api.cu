@@ -50,7 +50,7 @@ struct Ctx {
     cudaStream_t copy = nullptr;           // device->host copies run here so they overlap the next batch's kernels
     cudaEvent_t sized = nullptr;           // recorded behind the size publication of a run
     int64_t launches = 0;
-    bool profile = false;
+    uint32_t profile = 0;                  // bit s: stage s is timed
     double stage_ms[SHB_N_STAGES] = {};
     int64_t stage_launches[SHB_N_STAGES] = {};
     struct Pending { cudaEvent_t a, b; int stage; int n; };
@@ -110,7 +110,7 @@ template <class T> void dfree(T*& p, cudaStream_t st) { if (p) { cudaFreeAsync((
 
 struct StageTimer {
     int stage; cudaEvent_t a = nullptr, b = nullptr; bool on;
-    explicit StageTimer(int s) : stage(s), on(g.profile) {
+    explicit StageTimer(int s) : stage(s), on((g.profile >> s) & 1u) {
         if (!on) return;
         auto get = [] { cudaEvent_t e; if (!g.ev_free.empty()) { e = g.ev_free.back(); g.ev_free.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
@@ -226,7 +226,10 @@ SHB_API int shb_trim(void) {
 }
 
 SHB_API int shb_profile_enable(int on) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu); g.profile = on != 0; return SHB_OK; }
+    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    g.profile = on == 0 ? 0u : (on == 1 ? (1u << SHB_N_STAGES) - 1u : ((uint32_t)on >> 1) & ((1u << SHB_N_STAGES) - 1u));
+    return SHB_OK;
+}
 
 SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launches[SHB_N_STAGES], int reset) {
     std::lock_guard<std::recursive_mutex> lk(g.mu);
