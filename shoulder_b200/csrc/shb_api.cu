@@ -371,7 +371,7 @@ SHB_API int shb_result_free(shb_result* r) {
     if (r->pending) { cudaStreamSynchronize(g.copy); r->pending = false; }
     cudaStream_t st = g.stream;
     ShbDev& d = r->d;
-    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
+    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
     dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.totals, st); dfree(d.totals64, st);
     dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
     dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
@@ -423,7 +423,8 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
 
     CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
     CK(dalloc(&d.inc, G, st)); CK(dalloc(&d.sort_off, G + 1, st)); CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cnt, G, st));
-    CK(dalloc(&d.tile_sum, (G + 4095) / 4096 + 1, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st));
+    const size_t n_tiles = ((size_t)G + 4095) / 4096;
+    CK(dalloc(&d.scan_state, 4 * n_tiles + 4, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st));
     CK(dalloc(&d.totals, 8, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
     CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
     CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
@@ -431,6 +432,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, ((size_t)G + 1) * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.totals, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d.scan_state, 0, (4 * n_tiles + 4) * sizeof(unsigned long long), st));
     CK(cudaMemcpyAsync(d.totals + SHB_T_BAD, b->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));   // slot 1: bad-face flag
 
     // shared-memory capacities (leave headroom for static shared memory)
@@ -507,7 +509,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
-    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.tile_sum, st);
+    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
     dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st);
     dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.scratch, st);
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
