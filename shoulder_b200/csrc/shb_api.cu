@@ -570,7 +570,6 @@ static int enqueue_fetch(shb_result* r, uint32_t mask) {
     int rc = fetch_plane(r);
     if (rc) return rc;
     if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
-    bool sync = false;
     if ((mask & SHB_OUT_SEGMENTS) && !r->have_seg) {
         if (!(r->mask & SHB_OUT_SEGMENTS)) return fail(SHB_E_STATE, "segments / face_index were not in the outputs_mask of the run");
         const size_t S = r->W;                  // capacity: the exact count is seg_off[G], known once the plane arrays are in
@@ -578,13 +577,11 @@ static int enqueue_fetch(shb_result* r, uint32_t mask) {
         if (!r->h_face_index || !r->h_segments) return fail(SHB_E_NOMEM, "pinned host allocation failed");
         CK(cudaMemcpyAsync(r->h_face_index, r->d.face_index, S * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(r->h_segments, r->d.segments, S * 32, cudaMemcpyDeviceToHost, st));
-        r->have_seg = true; sync = true; r->pending = true;
+        r->have_seg = true; r->pending = true;
     }
     if ((mask & SHB_OUT_CONTOURS) && !r->have_cont) {
         const size_t G = r->G;
         ShbDev d = r->d;
-        ShbSweep* d_sw = nullptr;                       // compaction does not read sweeps, but keep ShbDev whole
-        (void)d_sw;
         CK(dalloc(&r->d_ct_off, G + 1, cst)); CK(dalloc(&r->d_pt_off, G + 1, cst));
         g.launches += shb_launch_scan_contours(d, r->d_ct_off, r->d_pt_off, cst);
         g.launches += shb_launch_publish(d.totals, 8, nullptr, g.h_totals, nullptr, cst);
@@ -605,7 +602,7 @@ static int enqueue_fetch(shb_result* r, uint32_t mask) {
         CK(cudaMemcpyAsync(r->h_pts, r->d_pts_c, (size_t)r->n_pts * 16, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(r->h_ctpt, r->d_ctpt_c, ((size_t)r->n_cont + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(r->h_ctarea, r->d_ctarea_c, (size_t)r->n_cont * 8, cudaMemcpyDeviceToHost, st));
-        r->have_cont = true; sync = true; r->pending = true;
+        r->have_cont = true; r->pending = true;
     }
     const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
                               SHB_OUT_ITR_CENTERED_START};
@@ -615,16 +612,15 @@ static int enqueue_fetch(shb_result* r, uint32_t mask) {
             r->h_prof[a] = pinned_get(r->prof_total * r->esz);
             if (!r->h_prof[a]) return fail(SHB_E_NOMEM, "pinned host allocation failed");
             CK(cudaMemcpyAsync(r->h_prof[a], r->d.prof[a], r->prof_total * r->esz, cudaMemcpyDeviceToHost, st));
-            sync = true; r->pending = true;
+            r->pending = true;
         }
     if ((mask & SHB_OUT_RADIAL) && !r->h_radial) {
         if (!r->d.radial) return fail(SHB_E_STATE, "radial image was not in the outputs_mask of the run");
         r->h_radial = pinned_get(r->rad_total * r->esz);
         if (!r->h_radial) return fail(SHB_E_NOMEM, "pinned host allocation failed");
         CK(cudaMemcpyAsync(r->h_radial, r->d.radial, r->rad_total * r->esz, cudaMemcpyDeviceToHost, st));
-        sync = true; r->pending = true;
+        r->pending = true;
     }
-    (void)sync;
     return SHB_OK;
 }
 
