@@ -452,6 +452,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     cap = d.stitch_cap; pcap = d.resample_cap;
     d.debug = 0;
     if (const char* f = getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= atoi(f) ? 1u : 0u;      // test hook
+    if (const char* f = getenv("SHB_DEBUG_MINRANK_ORDER")) d.debug |= atoi(f) ? 2u : 0u;       // test hook: contour order by minimum rank
     // K1 sizes everything downstream: the candidate triangles per plane (an upper bound of the hits that is exact
     // except on planes through vertices) are published as soon as the bucket histograms are scanned, and the host
     // waits for them while the device goes on with the counting sort

@@ -46,3 +46,20 @@ def test_lumpy_solid(gpu_backend, seed):
     rep = compare_sweep(v, f, zs, int(rng.choice([37, 64, 100, 360])), n_angles=int(rng.choice([7, 72, 360])),
                         expect_all_closed=False)
     assert rep["segments"] > 1000 and rep["contours"] >= len(zs) - 8
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_scene_of_blobs(gpu_backend, seed):
+    """Several separate lumpy solids in one mesh: many contours per plane, so the order in which the reference starts
+    them (CPython's set, rebuilt as components are removed) is exercised well beyond two or three contours."""
+    rng = np.random.default_rng(500 + seed)
+    vs, fs, off = [], [], 0
+    for k in range(int(rng.integers(6, 13))):
+        v, f = lumpy(100 * seed + k, 2 + k % 2)
+        v = 0.35 * (v - v.mean(axis=0)) + np.array([rng.uniform(-60, 60), rng.uniform(-60, 60), rng.uniform(-3, 3)])
+        vs.append(v); fs.append(f + off); off += len(v)
+    v, f = np.vstack(vs), np.vstack(fs)
+    z = v[:, 2]
+    zs = np.linspace(np.percentile(z, 80), np.percentile(z, 20), 30)
+    rep = compare_sweep(v, f, zs, 48, n_angles=36, expect_all_closed=False)
+    assert rep["contours"] >= 4 * len(zs)

@@ -82,3 +82,49 @@ if __name__ == "__main__":
             bad += 1
             if bad < 5: print("MISMATCH n", n, "C", C, a[:6], b[:6])
     print("mismatches", bad, "of 3000")
+
+
+def pop_order_slots(n, comp):
+    """Same rule, restated the way the device code works (shb_pyset_warp): no table, only the current slot of every node
+    outside the first component and, during a rebuild, one bit per slot of the new table; a pop is a minimum search
+    over (slot - finger) mod size."""
+    members = {}
+    for i, c in enumerate(comp): members.setdefault(c, []).append(i)
+    c0 = comp[0]
+    rid = [i for i in range(n) if comp[i] != c0]          # ascending ids of the remaining nodes
+    alive = [True] * len(rid)
+    rslot = list(rid)                                     # slot == id in the table of the construction
+    mask = table_size_for(n) - 1
+    fill, used, finger = n, n - len(members[c0]), 1
+    starts = [0]
+    def rebuild():
+        nonlocal mask, fill
+        if fill - used <= mask // 4: return
+        order = sorted((k for k in range(len(rid)) if alive[k]), key=lambda k: rslot[k])
+        minused = used * 2 if used > 50000 else used * 4
+        ns = MINSIZE
+        while ns <= minused: ns <<= 1
+        mask = ns - 1
+        taken = set()
+        for k in order:
+            key = rid[k]; perturb = key; i = key & mask; found = None
+            while found is None:
+                ncand = 10 if i + LINEAR_PROBES <= mask else 1
+                for j in range(ncand):
+                    if i + j not in taken: found = i + j; break
+                if found is None:
+                    perturb >>= PERTURB_SHIFT
+                    i = (i * 5 + 1 + perturb) & mask
+            taken.add(found); rslot[k] = found
+        fill = used
+    rebuild()
+    while used > 0:
+        f = finger & mask
+        k = min((k for k in range(len(rid)) if alive[k]), key=lambda k: (rslot[k] - f) & mask)
+        starts.append(rid[k]); finger = rslot[k] + 1
+        c = comp[rid[k]]
+        for j in range(len(rid)):
+            if comp[rid[j]] == c: alive[j] = False
+        used -= len(members[c])
+        rebuild()
+    return starts
