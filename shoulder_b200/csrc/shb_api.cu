@@ -451,6 +451,14 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     }
     cap = d.stitch_cap; pcap = d.resample_cap;
     d.debug = 0;
+    {   // a multiplier near G / golden ratio, coprime with G
+        d.stitch_mul = 0;
+        if (G > 64 && !getenv("SHB_DEBUG_NO_PERMUTE")) {
+            uint32_t m = (uint32_t)(0.6180339887 * (double)G) | 1u;
+            while (std::gcd(m, G) != 1u) m += 2;
+            d.stitch_mul = m % G;
+        }
+    }
     if (const char* f = getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= atoi(f) ? 1u : 0u;      // test hook
     if (const char* f = getenv("SHB_DEBUG_MINRANK_ORDER")) d.debug |= atoi(f) ? 2u : 0u;       // test hook: contour order by minimum rank
     // K1 sizes everything downstream: the candidate triangles per plane (an upper bound of the hits that is exact

@@ -99,6 +99,7 @@ struct ShbDev {
     uint32_t  n_angles;
     uint32_t  outputs_mask;
     uint32_t  stitch_cap;        // largest n handled in shared memory
+    uint32_t  stitch_mul;        // CTA b stitches plane (b * stitch_mul) mod n_plane (coprime with n_plane; 0: identity)
     uint32_t  resample_cap;      // largest point count handled in shared memory
     uint32_t  debug;             // test hooks: bit 0 = radius image by the all-candidates path on every plane
 };
