@@ -74,7 +74,9 @@ enum shb_array {
     SHB_ARR_SEL,              /* int32  [P,2]      (contour id, point count) of the outline ixy uses     */
     SHB_ARR_FACE_INDEX,       /* int32  [S]        metadata['face_index'], basic|vertex|edge, ascending  */
     SHB_ARR_SEGMENTS,         /* f64    [S,2,2]    lines_2D                                              */
-    SHB_ARR_CONTOUR_OFF,      /* int64  [P+1]      first contour of each plane, sweep-relative           */
+    SHB_ARR_CONTOUR_OFF,      /* int64  [P+1]      first contour of each plane, sweep-relative.  Contours of a plane come
+                                                  in the reference's entity order and start at the reference's start node
+                                                  (trimesh graph.traversals: CPython set pop order) */
     SHB_ARR_CONTOUR_PT_OFF,   /* int64  [C+1]      first point of each contour in POINTS                 */
     SHB_ARR_CONTOUR_AREA,     /* f64    [C]        |area| of each closed polygon            slice.py:55-57 */
     SHB_ARR_POINTS,           /* f64    [Npts,2]   Path2D.discrete, CCW, closed (first == last)          */
