@@ -86,3 +86,14 @@ def test_radial_ray_parallel_path_equals_the_all_candidates_path(gpu_backend, bo
         del os.environ["SHB_DEBUG_RADIAL_GENERAL"]
     assert np.array_equal(fast, slow) and np.isfinite(fast).all() and (fast > 0).mean() > 0.9     # 0 = ray misses the outline
     assert np.array_equal(run_gpu(m.vertices, m.faces, zs, 64, mask, 7).array(_lib.ARR_RADIAL), slow7)     # few, wide rays
+
+
+def test_dense_sweep_with_several_contour_planes(gpu_backend, bone_obbs):
+    """1,531 planes over the trabecular bone: the ends of the bone and its cavities give planes with two and three
+    contours, whose order and start nodes follow CPython's set in the reference."""
+    m = bone_obbs("humerus_left_trab").mesh
+    z = m.vertices[:, 2]
+    zs = np.linspace(0.995 * z.max(), 0.995 * z.min(), 1531)
+    rep = compare_sweep(m.vertices, m.faces, zs, 128, n_angles=90, expect_all_closed=False)
+    assert rep["contours"] > len(zs) + 20 and rep["pts_bitexact"] and not rep["h4_exceptions"]
+    assert rep["max_rel"] < 1e-12
