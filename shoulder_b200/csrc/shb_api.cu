@@ -136,6 +136,7 @@ struct shb_batch {
     ShbSweep* d_sweep = nullptr; uint32_t* d_item_off = nullptr;
     double* h_sorted = nullptr; double* h_orig = nullptr; double* oz = nullptr;
     uint32_t *plane_out = nullptr, *plane_in = nullptr, *plane_sweep = nullptr;
+    uint32_t* stitch_order = nullptr;      // planes nearest the ends of their sweep first (see shb_batch_create)
     uint32_t* d_bad = nullptr;             // set by K0 when a face names a vertex outside its mesh; checked at the first run
     Staging* stage = nullptr;              // pinned copies of the library-built arrays, held until the upload has executed
     bool checked = false;
@@ -257,7 +258,7 @@ SHB_API int shb_batch_free(shb_batch* b) {
     if (b->stage) { cudaStreamSynchronize(st); delete b->stage; b->stage = nullptr; }
     dfree(b->d_bad, st);
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
-    dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->oz, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st);
+    dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->oz, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st); dfree(b->stitch_order, st);
     delete b;
     return SHB_OK;
 }
@@ -325,6 +326,22 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     }
     if (items >= (uint64_t)1 << 32) return fail(SHB_E_CAPACITY, "sum of faces over sweeps = %llu needs a split", (unsigned long long)items);
     item_off[n_sweep] = (uint32_t)items;
+    // Launch order of the stitcher: the planes nearest the two ends of their sweep first.  Sections with several
+    // contours (several times the work of a plain one) sit at the ends of a bone; started first, they are hidden behind
+    // the bulk of the launch instead of extending its tail.
+    std::vector<uint32_t> order(G64);
+    {
+        std::vector<double> endness(G64);
+        for (int s = 0; s < n_sweep; ++s) {
+            const int64_t p0 = height_off[s], P = height_off[s + 1] - p0;
+            for (int64_t i = 0; i < P; ++i) {
+                const int64_t r = (int64_t)pin[p0 + i] - p0;           // rank of the plane along the sweep axis
+                endness[p0 + i] = (double)std::min(r, P - 1 - r) / (double)std::max<int64_t>(P, 1);
+            }
+        }
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return endness[a] < endness[c]; });
+    }
     b->n_item = (uint32_t)items; b->prof_total = prof;
 
     cudaStream_t st = g.stream;
@@ -338,6 +355,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     CK(dalloc(&b->d_sweep, n_sweep, st)); CK(dalloc(&b->d_item_off, n_sweep + 1, st));
     CK(dalloc(&b->h_sorted, G64, st)); CK(dalloc(&b->h_orig, G64, st)); CK(dalloc(&b->oz, G64, st));
     CK(dalloc(&b->plane_out, G64, st)); CK(dalloc(&b->plane_in, G64, st)); CK(dalloc(&b->plane_sweep, G64, st));
+    CK(dalloc(&b->stitch_order, G64, st));
     double T1 = now();
     CK(cudaMemcpyAsync(raw_v, verts, 3 * (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(raw_f, faces, 3 * (size_t)nf * sizeof(int64_t), cudaMemcpyHostToDevice, st));
@@ -354,6 +372,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     CK(stage.copy(b->plane_out, pout.data(), G64 * sizeof(uint32_t), st));
     CK(stage.copy(b->plane_in, pin.data(), G64 * sizeof(uint32_t), st));
     CK(stage.copy(b->plane_sweep, psw.data(), G64 * sizeof(uint32_t), st));
+    CK(stage.copy(b->stitch_order, order.data(), G64 * sizeof(uint32_t), st));
     double T2 = now();
     g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, b->d_bad, st);
     CK(cudaGetLastError());
@@ -451,16 +470,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     }
     cap = d.stitch_cap; pcap = d.resample_cap;
     d.debug = 0;
-    {   // a multiplier near G / golden ratio, coprime with G
-        d.stitch_mul = 0;
-        if (G > 64 && !getenv("SHB_DEBUG_NO_PERMUTE")) {
-            uint32_t m = (uint32_t)(0.6180339887 * (double)G) | 1u;
-            while (std::gcd(m, G) != 1u) m += 2;
-            d.stitch_mul = m % G;
-        }
-    }
-    if (const char* f = getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= atoi(f) ? 1u : 0u;      // test hook
-    if (const char* f = getenv("SHB_DEBUG_MINRANK_ORDER")) d.debug |= atoi(f) ? 2u : 0u;       // test hook: contour order by minimum rank
+    d.stitch_order = getenv("SHB_DEBUG_NO_PERMUTE") ? nullptr : b->stitch_order;
     // K1 sizes everything downstream: the candidate triangles per plane (an upper bound of the hits that is exact
     // except on planes through vertices) are published as soon as the bucket histograms are scanned, and the host
     // waits for them while the device goes on with the counting sort

@@ -57,6 +57,7 @@ struct ShbDev {
     const uint32_t* plane_out;   // [G] sorted plane -> original global plane
     const uint32_t* plane_in;    // [G] original global plane -> sorted plane
     const uint32_t* plane_sweep; // [G] sweep of sorted plane
+    const uint32_t* stitch_order;// [G] CTA b of the stitch launch takes plane stitch_order[b]: sweep ends first (nullptr: identity)
     uint32_t n_sweep, n_plane /*G*/, n_item;
     // ---- per-run scratch
     uint32_t* item_lo;    // [n_item] first sorted plane of the triangle's range
@@ -99,7 +100,6 @@ struct ShbDev {
     uint32_t  n_angles;
     uint32_t  outputs_mask;
     uint32_t  stitch_cap;        // largest n handled in shared memory
-    uint32_t  stitch_mul;        // CTA b stitches plane (b * stitch_mul) mod n_plane (coprime with n_plane; 0: identity)
     uint32_t  resample_cap;      // largest point count handled in shared memory
     uint32_t  debug;             // test hooks: bit 0 = radius image by the all-candidates path on every plane
 };
