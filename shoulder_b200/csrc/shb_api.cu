@@ -391,7 +391,7 @@ SHB_API int shb_result_free(shb_result* r) {
     cudaStream_t st = g.stream;
     ShbDev& d = r->d;
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
-    dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.totals, st); dfree(d.totals64, st);
+    dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.cap_sorted, st); dfree(d.totals, st); dfree(d.totals64, st);
     dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
     dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
     dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
@@ -443,7 +443,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
     CK(dalloc(&d.inc, G, st)); CK(dalloc(&d.sort_off, G + 1, st)); CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cnt, G, st));
     const size_t n_tiles = ((size_t)G + 4095) / 4096;
-    CK(dalloc(&d.scan_state, 4 * n_tiles + 4, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st));
+    CK(dalloc(&d.scan_state, 4 * n_tiles + 4, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st)); CK(dalloc(&d.cap_sorted, G, st));
     CK(dalloc(&d.totals, 8, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
     CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
     CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
@@ -530,7 +530,7 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
     dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st);
-    dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.scratch, st);
+    dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.cap_sorted, st); dfree(d.scratch, st);
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
     CK(cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming));
     CK(cudaEventRecord(r->done, st));

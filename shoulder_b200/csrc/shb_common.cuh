@@ -68,6 +68,7 @@ struct ShbDev {
     uint32_t* dec;        // [G+1] #triangles whose range ends before (sorted) plane
     uint32_t* cnt;        // [G]   candidate triangles per sorted plane (ranges covering it) >= exact hits
     uint32_t* cap_off;    // [G+1] hit-list offsets by candidate capacity, original plane order
+    uint32_t* cap_sorted; // [G]   the same offsets indexed by sorted plane (what the intersect kernel has at hand)
     unsigned long long* scan_state;   // [4][ceil(G/4096)] tile aggregates of the four scans of a run + 4 tile tickets, zeroed per run
     uint32_t* totals;     // [8]   M, -, -, S, maxn, nbig, ...
     uint4*    rec;        // [n_item] bucketed triangles (face, lo, span, sweep); first M are live
