@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SHB_ABI_VERSION 1
+#define SHB_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SHB_API __attribute__((visibility("default")))
@@ -106,15 +106,33 @@ enum shb_array {
 #define SHB_ST_SPLIT_COPY   0x10u  /* two copies of one node round differently (H4-ii)             */
 #define SHB_ST_GENERAL      0x20u  /* internal consistency check of the contour ranking failed; contours of the plane
                                       are incomplete (never observed; kept as a guard instead of an out-of-bounds write) */
+#define SHB_ST_MERGED       0x40u  /* trimesh Path.__init__ -> merge_vertices fused contour nodes of this plane: consecutive nodes
+                                      whose coordinates round equal at digits = |int(log10(1e-8 * scale))| (closer than ~1e-6 mm
+                                      on a 10..100 mm section); the delivered contour has fewer points than the plane has segments */
 
 typedef struct shb_batch  shb_batch;
 typedef struct shb_result shb_result;
+
+/* Per-sweep request of shb_batch_run_req: which windowed outputs a sweep wants and over which of its planes.
+ * Index a = 0..5: the profile arrays in SHB_ARR_IXY .. SHB_ARR_ITR_CENTERED_START order; a = 6: the radius image.
+ * Rows [row_lo[a], row_hi[a]) of the sweep are computed and delivered for array a (row_hi < 0: to the last plane) — the
+ * consumers' fractional windows (slice.py:157-164: anatomic_neck.py:34 reads 512 of the 600 proximal rows of itr_start,
+ * bicipital_groove.py:161 reads 330 of itr_centered_start, canal.py / surgical_neck.py read no profile at all).  Plane
+ * records (SHB_OUT_PLANE) always cover every plane.  Replaces nothing in the reference, which computes every row. */
+#define SHB_N_WINDOWED 7
+typedef struct shb_sweep_request {
+    uint32_t outputs_mask;                 /* SHB_OUT_IXY .. SHB_OUT_ITR_CENTERED_START, SHB_OUT_RADIAL bits of this sweep */
+    int32_t  row_lo[SHB_N_WINDOWED];
+    int32_t  row_hi[SHB_N_WINDOWED];
+} shb_sweep_request;
 
 /* Library / device bring-up.  device = CUDA ordinal for this process (one process per GPU).
  * Idempotent.  Replaces nothing in the reference (it is CPU-only). */
 SHB_API int shb_init(int device);
 
-/* Kernels are enqueued on this stream (a cudaStream_t; NULL = the library's own stream). */
+/* Kernels are enqueued on this stream (a cudaStream_t; NULL = the library's own stream).  A batch and a result belong to
+ * the stream that was current when they were made: later runs on another stream wait for the batch's upload, and their
+ * device memory is released on their own stream behind the last work that used it. */
 SHB_API int shb_set_stream(void* cuda_stream);
 
 /* Upload a batch of meshes and the sweeps to run on them; inputs become HBM-resident.
@@ -141,6 +159,13 @@ SHB_API int shb_batch_free(shb_batch* batch);
  * stitch -> resample/unroll.  Results stay on the device until fetched.
  * Replaces slice.py:21-29 (_slices) and the loops of slice.py:34-147. */
 SHB_API int shb_batch_run(shb_batch* batch, uint32_t outputs_mask, int32_t n_angles, shb_result** out);
+
+/* Same with one request per sweep (req[n_sweep]; NULL = every sweep takes outputs_mask over all its planes).  The
+ * SEGMENTS / CONTOURS / F32 bits of outputs_mask apply to the whole batch.  shb_result_array then hands back only the
+ * rows of each sweep's window (shape[0] = row_hi - row_lo); shb_result_window tells which. */
+SHB_API int shb_batch_run_req(shb_batch* batch, const shb_sweep_request* req, uint32_t outputs_mask, int32_t n_angles,
+                              shb_result** out);
+SHB_API int shb_result_window(const shb_result* result, int32_t which, int32_t sweep, int32_t* row_lo, int32_t* row_hi);
 
 /* One-call form with host buffers in and out (create + run + fetch of outputs_mask + free). */
 SHB_API int shb_sweep_batch(int32_t n_mesh,

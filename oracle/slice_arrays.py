@@ -72,14 +72,14 @@ def chosen_outline(path) -> np.ndarray:
 class OracleSlices:
     """All cached arrays of ``slice.Slices`` for one sweep, from oracle paths."""
 
-    def __init__(self, vertices, faces, zs, interp_num, merge="hash", version="4", return_odd=False):
+    def __init__(self, vertices, faces, zs, interp_num, merge="hash", version="4", return_odd=False, **section_kw):
         self.zs_all = np.asarray(zs, dtype=np.float64)
         self.interp_num = int(interp_num)
         self.return_odd = return_odd
         self.z_orig = np.mean(self.zs_all)
         self.z_incrs = self.zs_all - self.z_orig
         self.paths = tp.section_multiplane(vertices, faces, [0, 0, self.z_orig], [0, 0, 1], self.z_incrs,
-                                           merge=merge, version=version)
+                                           merge=merge, version=version, **section_kw)
         self._cache = {}
 
     def _get(self, name, fn):
@@ -146,6 +146,18 @@ class OracleSlices:
     def window(self, arr, cutoff):
         lo, hi = cutoff_window(len(arr), cutoff, self.return_odd)
         return arr[lo:hi]
+
+
+def rows_for_paths(paths, interp_num: int) -> dict:
+    """The per-plane rows of every cached array for an arbitrary list of (non-None, closed) paths — what
+    ``Slices`` would hold if its sweep consisted of just these planes (slice.py:34-147 is row-wise)."""
+    class _Sub(OracleSlices):
+        def __init__(self, paths, n):
+            self.paths, self.interp_num, self.return_odd, self._cache = paths, int(n), False, {}
+    s = _Sub(list(paths), interp_num)
+    areas = np.array([max(q.area for q in p.polygons_closed) if len(p.entities) > 1 else p.area for p in s.paths])
+    return {"areas1": areas, "centroids": s.centroids, "ixy": s.ixy, "ixy_centered": s.ixy_centered, "itr": s.itr,
+            "itr_start": s.itr_start, "itr_centered": s.itr_centered, "itr_centered_start": s.itr_centered_start}
 
 
 def radial_image(paths, n_angles: int) -> np.ndarray:

@@ -207,22 +207,7 @@ def hashable_rows(data, version: str = "4"):
     q = float_to_int(data)
     if len(q) == 0:
         return np.zeros(0, dtype=np.uint64), True
-    threshold = 2 ** 31
-    if version == "4":
-        if q.max() < threshold and q.min() > -threshold:
-            bang = (q.T + (threshold + 1)).astype(np.uint64)
-            h = np.zeros(len(q), dtype=np.uint64)
-            for offset, col in enumerate(bang):
-                np.bitwise_xor(h, col << np.uint64(offset * 32), out=h)
-            return h, True
-    else:
-        if np.abs(q).max() < threshold:
-            h = np.zeros(len(q), dtype=np.int64)
-            for offset, col in enumerate(q.T):
-                np.bitwise_xor(h, col << (offset * 32), out=h)
-            return h, True
-    void = np.ascontiguousarray(q).view(np.dtype((np.void, q.dtype.itemsize * q.shape[1]))).reshape(-1)
-    return void, False
+    return _hash_int_rows(q, version)
 
 
 def rank_key(points, packed: bool, version: str = "4"):
@@ -351,6 +336,139 @@ def lines_to_path(segments_2d: np.ndarray, keys=None, merge: str = "hash", versi
 
 
 # --------------------------------------------------------------------------------------
+# path.Path.__init__(process=True): merge_vertices / remove_duplicate_entities / remove_unreferenced_vertices
+# --------------------------------------------------------------------------------------
+def decimal_to_digits(decimal: float, min_digits=None) -> int:
+    """trimesh ``util.decimal_to_digits``: ``abs(int(log10(decimal)))`` (int() truncates towards zero)."""
+    digits = abs(int(np.log10(decimal)))
+    if min_digits is not None:
+        digits = int(np.clip(digits, min_digits, 20))
+    return int(digits)
+
+
+def path_scale(vertices: np.ndarray) -> float:
+    """trimesh ``Path.scale``: length of the diagonal of the vertices' bounding box."""
+    return float((np.ptp(vertices, axis=0) ** 2).sum() ** 0.5)
+
+
+def merge_runs(idx: np.ndarray) -> np.ndarray:
+    """trimesh ``grouping.merge_runs`` on an index sequence: consecutive repeats collapse to one."""
+    idx = np.asarray(idx, dtype=np.int64)
+    if len(idx) == 0:
+        return idx
+    keep = np.ones(len(idx), dtype=bool)
+    keep[1:] = idx[1:] != idx[:-1]
+    return idx[keep]
+
+
+def process_path(vertices: np.ndarray, entities, version: str = "4"):
+    """What ``load_path`` does to the output of ``lines_to_path`` by constructing ``Path2D(..., process=True)``:
+
+    ``merge_vertices``: vertices whose coordinates round equal at ``digits = decimal_to_digits(tol.merge * scale,
+    min_digits=1)`` (6 digits for a section 10..100 mm across, i.e. closer than ~1e-6 mm) become one vertex — the
+    first in vertex order is kept, the vertex array is re-ordered by the hash of the rounded rows — and runs of
+    repeated indices inside an entity collapse; a 3-point loop a-b-a becomes the line a-b, entities with fewer
+    than two points are dropped.  ``remove_duplicate_entities`` and ``remove_unreferenced_vertices`` follow.
+    Returns (vertices, entities, n_merged).  On the reference's test bones n_merged == 0 on every plane
+    (tests/test_oracle_process.py), i.e. the step renumbers vertices and changes nothing the consumers read.
+    """
+    vertices = np.asarray(vertices, dtype=np.float64)
+    if len(vertices) == 0:
+        return vertices, list(entities), 0
+    digits = decimal_to_digits(TOL_MERGE * path_scale(vertices), min_digits=1)
+    q = np.round(vertices * 10 ** digits - 1e-6).astype(np.int64)             # grouping.float_to_int(data, digits)
+    h, _ = _hash_int_rows(q, version)
+    _, unique, inverse = np.unique(h, return_index=True, return_inverse=True)
+    inverse = inverse.reshape(-1)
+    n_merged = len(vertices) - len(unique)
+    out = []
+    for e in entities:
+        pts = merge_runs(inverse[np.asarray(e, dtype=np.int64)])
+        if len(pts) == 3 and pts[0] == pts[-1]:
+            pts = pts[:2]
+        elif len(pts) < 2:
+            continue
+        out.append(pts)
+    new_vertices = vertices[unique]
+    # remove_duplicate_entities: entities with identical point lists (either direction for closed loops hash
+    # differently in trimesh, so only exact repeats are dropped)
+    seen, dedup = set(), []
+    for pts in out:
+        key = pts.tobytes()
+        if key in seen:
+            continue
+        seen.add(key)
+        dedup.append(pts)
+    # remove_unreferenced_vertices
+    if dedup:
+        ref = np.unique(np.concatenate(dedup))
+        remap = -np.ones(len(new_vertices), dtype=np.int64)
+        remap[ref] = np.arange(len(ref))
+        dedup = [remap[pts] for pts in dedup]
+        new_vertices = new_vertices[ref]
+    return new_vertices, dedup, n_merged
+
+
+def _hash_int_rows(q: np.ndarray, version: str = "4"):
+    """``hashable_rows`` on already-integer rows (see :func:`hashable_rows`)."""
+    threshold = 2 ** 31
+    if version == "4":
+        if q.max() < threshold and q.min() > -threshold:
+            bang = (q.T + (threshold + 1)).astype(np.uint64)
+            h = np.zeros(len(q), dtype=np.uint64)
+            for offset, col in enumerate(bang):
+                np.bitwise_xor(h, col << np.uint64(offset * 32), out=h)
+            return h, True
+    else:
+        if np.abs(q).max() < threshold:
+            h = np.zeros(len(q), dtype=np.int64)
+            for offset, col in enumerate(q.T):
+                np.bitwise_xor(h, col << (offset * 32), out=h)
+            return h, True
+    void = np.ascontiguousarray(q).view(np.dtype((np.void, q.dtype.itemsize * q.shape[1]))).reshape(-1)
+    return void, False
+
+
+# --------------------------------------------------------------------------------------
+# shapely / GEOS validity of a ring (path.polygons.paths_to_polygons keeps a polygon only if ``is_valid``)
+# --------------------------------------------------------------------------------------
+def ring_is_valid(xy: np.ndarray) -> bool:
+    """GEOS ``IsValidOp`` for a polygon that has only a shell: the closed ring must not cross or touch itself.
+    Every pair of non-adjacent edges is tested with orientation signs (O(m^2), vectorised); adjacent edges may
+    only share their common vertex (a collinear fold-back is a self-intersection)."""
+    xy = np.asarray(xy, dtype=np.float64)
+    if len(xy) < 4 or not np.array_equal(xy[0], xy[-1]) or not np.isfinite(xy).all():
+        return False
+    p, q = xy[:-1], xy[1:]
+    m = len(p)
+    if (np.abs(q - p).sum(axis=1) == 0).all():
+        return False
+
+    def orient(a, b, c):
+        return np.sign((b[..., 0] - a[..., 0]) * (c[..., 1] - a[..., 1]) - (b[..., 1] - a[..., 1]) * (c[..., 0] - a[..., 0]))
+
+    i, j = np.triu_indices(m, k=2)
+    keep = ~((i == 0) & (j == m - 1))                      # first and last edge are adjacent through the closing vertex
+    i, j = i[keep], j[keep]
+    a, b, c, d = p[i], q[i], p[j], q[j]
+    o1, o2, o3, o4 = orient(a, b, c), orient(a, b, d), orient(c, d, a), orient(c, d, b)
+    proper = (o1 * o2 < 0) & (o3 * o4 < 0)
+
+    def on_seg(a, b, c, o):                                 # c collinear with a-b and inside its box
+        return (o == 0) & (np.minimum(a[:, 0], b[:, 0]) <= c[:, 0]) & (c[:, 0] <= np.maximum(a[:, 0], b[:, 0])) & \
+               (np.minimum(a[:, 1], b[:, 1]) <= c[:, 1]) & (c[:, 1] <= np.maximum(a[:, 1], b[:, 1]))
+    touch = on_seg(a, b, c, o1) | on_seg(a, b, d, o2) | on_seg(c, d, a, o3) | on_seg(c, d, b, o4)
+    if (proper | touch).any():
+        return False
+    # adjacent edges: fold-back along the same line
+    nxt = np.r_[np.arange(1, m), 0]
+    u, w = q - p, q[nxt] - p[nxt]
+    cross = u[:, 0] * w[:, 1] - u[:, 1] * w[:, 0]
+    dot = u[:, 0] * w[:, 0] + u[:, 1] * w[:, 1]
+    return not bool(((cross == 0) & (dot < 0)).any())
+
+
+# --------------------------------------------------------------------------------------
 # path.Path2D — the attributes the reference consumes
 # --------------------------------------------------------------------------------------
 def ring_area_signed(xy: np.ndarray) -> float:
@@ -386,6 +504,7 @@ class OraclePolygon:
     def __init__(self, ring: np.ndarray):
         self.ring = ring
         self.area = abs(ring_area_signed(ring))
+        self.valid = True
 
     @property
     def exterior_coords(self):
@@ -398,11 +517,12 @@ class OraclePath2D:
     ``epicondyle.py:36,43``), ``area`` (``:59``), ``centroid`` (``:38``; ``canal.py:46``), ``bounds``,
     ``vertices`` (``mesh.py:102``) and ``metadata['face_index']``."""
 
-    def __init__(self, vertices, entities, metadata=None, info=None):
+    def __init__(self, vertices, entities, metadata=None, info=None, validate=True):
         self.vertices = vertices
         self.entities = entities
         self.metadata = metadata or {}
         self.info = info or {}
+        self.validate = validate
 
     def entity_closed(self, i) -> bool:
         e = self.entities[i]
@@ -427,7 +547,27 @@ class OraclePath2D:
 
     @property
     def polygons_closed(self):
-        return [OraclePolygon(d) if len(d) >= 4 else None for d in self.discrete]
+        """trimesh ``paths_to_polygons``: a polygon per closed path with >= 4 points.  trimesh keeps it as is when
+        shapely calls it valid and otherwise hands it to ``repair_invalid`` (GEOS ``buffer`` tricks), which cannot be
+        restated without GEOS: such a ring keeps its un-repaired polygon here (``valid = False``; shapely's ``area``
+        of an invalid polygon is still the shoelace sum) and is listed in ``info['invalid_rings']``.  It happens on
+        the reference's own test bones — CT surfaces self-intersect a little (e.g. humerus_left, DistalSlices
+        plane 15 at 30 planes: two edges three apart cross) — and moves the area by the size of the tiny loop."""
+        cached = getattr(self, "_polys", None)
+        if cached is not None:
+            return cached
+        out = []
+        for k, d in enumerate(self.discrete):
+            if len(d) < 4:
+                out.append(None)
+                continue
+            poly = OraclePolygon(d)
+            if self.validate and not ring_is_valid(d):
+                poly.valid = False
+                self.info.setdefault("invalid_rings", []).append(k)
+            out.append(poly)
+        self._polys = out
+        return out
 
     @property
     def bounds(self):
@@ -456,8 +596,11 @@ class OraclePath2D:
 
 
 def section_multiplane(vertices, faces, plane_origin, plane_normal, heights, merge="hash", version="4",
-                       check_merge=True):
-    """trimesh ``Trimesh.section_multiplane``: list of P paths, ``None`` where a plane misses."""
+                       check_merge=True, process=True, validate=True):
+    """trimesh ``Trimesh.section_multiplane``: list of P paths, ``None`` where a plane misses.
+    ``process``: apply ``Path.__init__``'s processing (:func:`process_path`); ``validate``: shapely's ``is_valid``
+    gate of ``polygons_closed``.  ``check_merge=False`` skips the oracle-only comparison of the two merge rules
+    (what the timed CPU arm uses: the reference does no such work)."""
     segs, transforms, fidx, keys, klass = mesh_multiplane(vertices, faces, plane_origin, plane_normal, heights)
     paths = [None] * len(segs)
     for i in range(len(segs)):
@@ -465,6 +608,8 @@ def section_multiplane(vertices, faces, plane_origin, plane_normal, heights, mer
             continue
         kk = keys[i] if (check_merge or merge == "topo") else None
         verts, ents, info = lines_to_path(segs[i], kk, merge=merge, version=version)
-        paths[i] = OraclePath2D(verts, ents, info=info, metadata={
+        if process:
+            verts, ents, info["n_merged"] = process_path(verts, ents, version)
+        paths[i] = OraclePath2D(verts, ents, info=info, validate=validate, metadata={
             "to_3D": transforms[i], "face_index": fidx[i], "segments": segs[i], "keys": keys[i], "klass": klass[i]})
     return paths

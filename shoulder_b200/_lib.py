@@ -13,7 +13,7 @@ import numpy as np
 LIB_PATH = Path(__file__).resolve().parent / "libshoulder_b200.so"
 
 # --- constants mirrored from include/shoulder_b200.h ---------------------------------------
-ABI_VERSION = 1
+ABI_VERSION = 2
 OUT_PLANE, OUT_SEGMENTS, OUT_CONTOURS = 0x001, 0x002, 0x004
 OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START = 0x008, 0x010, 0x020, 0x040
 OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL = 0x080, 0x100, 0x200
@@ -22,13 +22,16 @@ OUT_F32 = 0x400
 (ARR_N_SEG, ARR_SEG_OFF, ARR_N_ENT, ARR_STATUS, ARR_BOUNDS, ARR_CENTROID, ARR_AREA1, ARR_SEL, ARR_FACE_INDEX,
  ARR_SEGMENTS, ARR_CONTOUR_OFF, ARR_CONTOUR_PT_OFF, ARR_CONTOUR_AREA, ARR_POINTS, ARR_IXY, ARR_IXY_CENTERED, ARR_ITR,
  ARR_ITR_START, ARR_ITR_CENTERED, ARR_ITR_CENTERED_START, ARR_RADIAL, ARR_COUNT) = range(22)
-ST_EMPTY, ST_OPEN, ST_NONMANIFOLD, ST_RANK_TIE, ST_SPLIT_COPY, ST_GENERAL = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+ST_EMPTY, ST_OPEN, ST_NONMANIFOLD, ST_RANK_TIE, ST_SPLIT_COPY, ST_GENERAL, ST_MERGED = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
+N_WINDOWED = 7                       # six profile arrays + the radius image (shb_sweep_request)
+WINDOWED_BITS = (OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START, OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL)
 N_STAGES = 7
 STAGE_NAMES = ("bucket", "scan", "scatter", "intersect", "scan2", "stitch", "resample")
 _DTYPES = {1: np.int32, 2: np.int64, 3: np.uint32, 4: np.float64, 5: np.float32}
 
 EXPORTS = (
-    "shb_init", "shb_set_stream", "shb_batch_create", "shb_batch_free", "shb_batch_run", "shb_sweep_batch",
+    "shb_init", "shb_set_stream", "shb_batch_create", "shb_batch_free", "shb_batch_run", "shb_batch_run_req", "shb_result_window",
+    "shb_sweep_batch",
     "shb_result_fetch", "shb_result_fetch_async", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
 )
@@ -58,6 +61,8 @@ def load() -> C.CDLL:
     lib.shb_batch_create.argtypes = [i32, p, p, p, p, i32, p, p, p, p, p, pp]
     lib.shb_batch_free.argtypes = [p]
     lib.shb_batch_run.argtypes = [p, u32, i32, pp]
+    lib.shb_batch_run_req.argtypes = [p, p, u32, i32, pp]
+    lib.shb_result_window.argtypes = [p, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     lib.shb_sweep_batch.argtypes = [i32, p, p, p, p, i32, p, p, p, p, p, u32, i32, pp]
     lib.shb_result_fetch.argtypes = [p, u32]
     lib.shb_result_fetch_async.argtypes = [p, u32]
@@ -130,6 +135,30 @@ def _ptr(a: np.ndarray):
     return C.c_void_p(a.ctypes.data)
 
 
+class SweepRequest(C.Structure):
+    """``shb_sweep_request``: the windowed outputs one sweep wants and the plane rows they cover."""
+    _fields_ = [("outputs_mask", C.c_uint32), ("row_lo", C.c_int32 * N_WINDOWED), ("row_hi", C.c_int32 * N_WINDOWED)]
+
+
+def make_requests(specs):
+    """specs: per sweep either an int mask (all rows) or a dict {OUT_* bit: (row_lo, row_hi)}."""
+    arr = (SweepRequest * len(specs))()
+    for k, spec in enumerate(specs):
+        if isinstance(spec, dict):
+            arr[k].outputs_mask = 0
+            for a, bit in enumerate(WINDOWED_BITS):
+                arr[k].row_lo[a], arr[k].row_hi[a] = 0, -1
+                if bit in spec:
+                    lo, hi = spec[bit]
+                    arr[k].outputs_mask |= bit
+                    arr[k].row_lo[a], arr[k].row_hi[a] = int(lo), int(hi)
+        else:
+            arr[k].outputs_mask = int(spec)
+            for a in range(N_WINDOWED):
+                arr[k].row_lo[a], arr[k].row_hi[a] = 0, -1
+    return arr
+
+
 class SweepResult:
     """Owner of one ``shb_result``.  Arrays are numpy views of backend-owned pinned memory and
     stay valid while this object is alive."""
@@ -153,6 +182,12 @@ class SweepResult:
         buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
         buf._shb_owner = self            # arr.base -> buf -> self keeps the pinned memory alive
         return np.frombuffer(buf, dtype=dtype).reshape(shp)   # a view, like the reference's cached arrays
+
+    def window(self, which: int, sweep: int = 0):
+        """(row_lo, row_hi) of the sweep's planes that array ``which`` covers in this result."""
+        lo, hi = C.c_int32(), C.c_int32()
+        check(load().shb_result_window(self._h, which, sweep, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
 
     def fetch(self, mask: int) -> None:
         check(load().shb_result_fetch(self._h, mask))
@@ -210,9 +245,15 @@ class SweepBatch:
                                       _ptr(a[4]), _ptr(a[5]), _ptr(a[6]), _ptr(a[7]), _ptr(a[8]), C.byref(h)))
         self._h = h
 
-    def run(self, outputs_mask: int, n_angles: int = 0) -> SweepResult:
+    def run(self, outputs_mask: int, n_angles: int = 0, requests=None) -> SweepResult:
+        """``requests``: optional per-sweep list (see :func:`make_requests`) -> ``shb_batch_run_req``."""
         r = C.c_void_p()
-        check(load().shb_batch_run(self._h, outputs_mask, n_angles, C.byref(r)))
+        if requests is None:
+            check(load().shb_batch_run(self._h, outputs_mask, n_angles, C.byref(r)))
+        else:
+            assert len(requests) == self.n_sweep
+            req = requests if isinstance(requests, C.Array) else make_requests(requests)
+            check(load().shb_batch_run_req(self._h, C.cast(req, C.c_void_p), outputs_mask, n_angles, C.byref(r)))
         return SweepResult(r, self.n_sweep, keepalive=self)
 
     def close(self):
@@ -227,17 +268,19 @@ class SweepBatch:
             pass
 
 
-def sweep_batch(meshes, sweeps, outputs_mask: int, n_angles: int = 0, packed=None, lazy: bool = False) -> SweepResult:
+def sweep_batch(meshes, sweeps, outputs_mask: int, n_angles: int = 0, packed=None, lazy: bool = False, requests=None) -> SweepResult:
     """One-call host-to-host form (``shb_sweep_batch``).  ``lazy=True`` computes everything in
     ``outputs_mask`` on the device but copies an array to the host only when it is first asked for
     (``shb_batch_create`` + ``shb_batch_run``; the inputs are released right after the kernels are enqueued)."""
     init(_inited if _inited is not None else 0)
     a = packed if packed is not None else _pack(meshes, sweeps)
-    if lazy:
+    if lazy or requests is not None:
         batch = SweepBatch(None, None, packed=a)
-        res = batch.run(outputs_mask, n_angles)
+        res = batch.run(outputs_mask, n_angles, requests)
         res._keep = None
         batch.close()                     # stream ordered: the enqueued kernels still see the inputs
+        if not lazy:
+            res.fetch(outputs_mask | OUT_PLANE)
         return res
     r = C.c_void_p()
     check(load().shb_sweep_batch(len(a[1]) - 1, _ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), len(a[4]), _ptr(a[4]),
@@ -290,16 +333,17 @@ def split_packed(packed, n_chunks: int):
     return chunks, np.array(first, dtype=np.int64)
 
 
-def sweep_batch_pipelined(chunks, first_sweep, outputs_mask: int, n_angles: int = 0) -> PipelinedResult:
+def sweep_batch_pipelined(chunks, first_sweep, outputs_mask: int, n_angles: int = 0, requests=None) -> PipelinedResult:
     """Host-to-host call for a batch pre-cut into chunks (:func:`split_packed`): chunk i+1 is uploaded and
     computed while chunk i's outputs travel back over PCIe (the library copies on its own stream).  The
     device->host transfer dominates a large batch (16 bytes per sample), so hiding everything else behind
     it is the whole gain."""
     init(_inited if _inited is not None else 0)
     parts = []
-    for c in chunks:
+    for k, c in enumerate(chunks):
         batch = SweepBatch(None, None, packed=c)
-        res = batch.run(outputs_mask, n_angles)
+        req = None if requests is None else requests[int(first_sweep[k]):int(first_sweep[k + 1])]
+        res = batch.run(outputs_mask, n_angles, req)
         res._keep = None
         batch.close()
         res.fetch_async(outputs_mask)        # copy stream: starts as soon as this group's kernels finish

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <ctime>
+#include <unistd.h>
 #include <cstring>
 #include <memory>
 #include <type_traits>
@@ -60,8 +61,21 @@ struct Ctx {
     uint32_t* h_totals = nullptr;          // pinned readback slot
     unsigned long long* h_totals64 = nullptr;
     double2* angle_tab = nullptr; int angle_n = 0;
-    size_t pinned_limit = (size_t)16 << 30;   // bytes of pinned host cache kept across calls (SHB_PINNED_LIMIT_MB)
+    size_t pinned_limit = (size_t)4 << 30;    // bytes of pinned host cache kept across calls: min(16 GiB, RAM / 4) at init, SHB_PINNED_LIMIT_MB
+    cudaMemPool_t pool = nullptr;             // the library's OWN stream-ordered pool (the device's default pool is left alone)
 } g;
+
+// CUDA's current device is per host thread: every entry point switches to the library's device for its duration, so a
+// call from a thread that never saw shb_init (or that works on another GPU) still launches where the streams live
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    DeviceGuard() {
+        if (!g.inited) return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != g.device) switched = cudaSetDevice(g.device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define SHB_ENTER std::lock_guard<std::recursive_mutex> lk(g.mu); DeviceGuard dg_
 
 void* pinned_get(size_t bytes) {
     if (bytes == 0) bytes = 16;
@@ -104,22 +118,25 @@ struct Staging {
 };
 
 template <class T> cudaError_t dalloc(T** p, size_t n, cudaStream_t st) {
-    return cudaMallocAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T), st);
+    return cudaMallocFromPoolAsync(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T), g.pool, st);
+}
+cudaError_t dalloc_bytes(void** p, size_t bytes, cudaStream_t st) {
+    return cudaMallocFromPoolAsync(p, std::max<size_t>(bytes, 16), g.pool, st);
 }
 template <class T> void dfree(T*& p, cudaStream_t st) { if (p) { cudaFreeAsync((void*)p, st); p = nullptr; } }
 
 struct StageTimer {
-    int stage; cudaEvent_t a = nullptr, b = nullptr; bool on;
-    explicit StageTimer(int s) : stage(s), on((g.profile >> s) & 1u) {
+    int stage; cudaEvent_t a = nullptr, b = nullptr; bool on; cudaStream_t st;
+    StageTimer(int s, cudaStream_t stream) : stage(s), on((g.profile >> s) & 1u), st(stream) {
         if (!on) return;
         auto get = [] { cudaEvent_t e; if (!g.ev_free.empty()) { e = g.ev_free.back(); g.ev_free.pop_back(); } else cudaEventCreate(&e); return e; };
         a = get(); b = get();
-        cudaEventRecord(a, g.stream);
+        cudaEventRecord(a, st);
     }
     void stop(int n_launch) {
         g.launches += n_launch;
         if (!on) return;
-        cudaEventRecord(b, g.stream);
+        cudaEventRecord(b, st);
         g.pending.push_back({a, b, stage, n_launch});
     }
 };
@@ -130,7 +147,6 @@ struct shb_batch {
     int32_t n_mesh = 0, n_sweep = 0;
     int64_t n_vert = 0, n_face = 0;
     uint32_t G = 0, n_item = 0, max_interp = 0;
-    uint64_t prof_total = 0;
     std::vector<ShbSweep> sweeps;          // host copy
     double4* vert = nullptr; double* vz = nullptr; int4* face = nullptr;
     ShbSweep* d_sweep = nullptr; uint32_t* d_item_off = nullptr;
@@ -140,13 +156,20 @@ struct shb_batch {
     uint32_t* d_bad = nullptr;             // set by K0 when a face names a vertex outside its mesh; checked at the first run
     Staging* stage = nullptr;              // pinned copies of the library-built arrays, held until the upload has executed
     bool checked = false;
+    // Stream ownership: the batch lives on the stream it was created on.  A run on another stream (shb_set_stream in
+    // between) waits for `uploaded`; the batch's memory is freed on its own stream behind `last_use` (the last run).
+    cudaStream_t stream = nullptr;
+    cudaEvent_t uploaded = nullptr, last_use = nullptr;
+    // compact launch list of the resample kernel for the last request that excluded planes (per-sweep windows)
+    uint32_t* rs_order = nullptr; uint32_t n_rs = 0; uint64_t rs_key = 0;
 };
 
 struct shb_result {
     const shb_batch* batch = nullptr;
     std::vector<ShbSweep> sweeps;
     uint32_t G = 0, mask = 0, n_angles = 0;
-    uint64_t prof_total = 0, rad_total = 0;
+    uint64_t arr_total[SHB_N_ARR] = {};     // elements of each windowed output array (profiles: rows x 2 x N summed over sweeps)
+    cudaStream_t stream = nullptr;          // the stream the result was computed on; its device memory is freed there
     uint32_t W = 0;                         // capacity of the per-segment arrays
     ShbDev d = {};                          // device pointers owned by the result
     cudaEvent_t done = nullptr;             // recorded on the compute stream when the result's kernels are enqueued
@@ -160,7 +183,7 @@ struct shb_result {
     uint32_t *h_status = nullptr, *h_seg_off = nullptr, *h_ct_off = nullptr, *h_pt_off = nullptr;
     double *h_bounds = nullptr, *h_centroid = nullptr, *h_area1 = nullptr, *h_segments = nullptr;
     double *h_pts = nullptr, *h_ctarea = nullptr; int64_t* h_ctpt = nullptr;
-    void* h_prof[6] = {}; void* h_radial = nullptr;
+    void* h_arr[SHB_N_ARR] = {};            // six profile arrays + the radius image
     size_t esz = 8;                         // bytes per profile / radius element
     std::vector<std::vector<int64_t>> rel;  // per-sweep relative offset arrays handed out
 };
@@ -172,7 +195,7 @@ SHB_API int shb_abi_version(void) { return SHB_ABI_VERSION; }
 SHB_API int64_t shb_launch_count(void) { return g.launches; }
 
 SHB_API int shb_init(int device) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (g.inited) {
         if (device != g.device) return fail(SHB_E_STATE, "already initialised on device %d", g.device);
         return SHB_OK;
@@ -193,10 +216,19 @@ SHB_API int shb_init(int device) {
     g.stream = g.own;
     CK(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&g.sized, cudaEventDisableTiming));
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    // a private pool: its "never release on its own" threshold must not leak into other users of cudaMallocAsync
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    CK(cudaMemPoolCreate(&g.pool, &props));
     uint64_t thr = UINT64_MAX;
-    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    CK(cudaMemPoolSetAttribute(g.pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    {   // page-locked host cache: a quarter of the host's RAM, at most 16 GiB
+        const long pages = sysconf(_SC_PHYS_PAGES), psz = sysconf(_SC_PAGE_SIZE);
+        if (pages > 0 && psz > 0) g.pinned_limit = std::min<size_t>((size_t)16 << 30, (size_t)pages * (size_t)psz / 4);
+    }
     if (const char* lim = getenv("SHB_PINNED_LIMIT_MB")) g.pinned_limit = (size_t)atoll(lim) << 20;
     CK(cudaHostAlloc(&g.h_totals, 8 * sizeof(uint32_t), cudaHostAllocMapped));       // written by k_publish, read after a stream sync
     CK(cudaHostAlloc(&g.h_totals64, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
@@ -205,20 +237,18 @@ SHB_API int shb_init(int device) {
 }
 
 SHB_API int shb_set_stream(void* cuda_stream) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     g.stream = cuda_stream ? (cudaStream_t)cuda_stream : g.own;
     return SHB_OK;
 }
 
 SHB_API int shb_trim(void) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     CK(cudaStreamSynchronize(g.stream));
     CK(cudaStreamSynchronize(g.copy));
-    cudaMemPool_t pool;
-    CK(cudaDeviceGetDefaultMemPool(&pool, g.device));
-    CK(cudaMemPoolTrimTo(pool, 0));
+    CK(cudaMemPoolTrimTo(g.pool, 0));
     for (size_t i = 0; i < g.pinned.size();) {
         if (!g.pinned[i].used) { cudaFreeHost(g.pinned[i].p); g.pinned[i] = g.pinned.back(); g.pinned.pop_back(); }
         else ++i;
@@ -227,13 +257,13 @@ SHB_API int shb_trim(void) {
 }
 
 SHB_API int shb_profile_enable(int on) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     g.profile = on == 0 ? 0u : (on == 1 ? (1u << SHB_N_STAGES) - 1u : ((uint32_t)on >> 1) & ((1u << SHB_N_STAGES) - 1u));
     return SHB_OK;
 }
 
 SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launches[SHB_N_STAGES], int reset) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     for (auto& p : g.pending) {
         CK(cudaEventSynchronize(p.b));
         float ms = 0.f;
@@ -252,13 +282,16 @@ SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launch
 }
 
 SHB_API int shb_batch_free(shb_batch* b) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!b) return SHB_OK;
-    cudaStream_t st = g.stream;
+    cudaStream_t st = b->stream ? b->stream : g.stream;
     if (b->stage) { cudaStreamSynchronize(st); delete b->stage; b->stage = nullptr; }
+    if (b->last_use) { cudaStreamWaitEvent(st, b->last_use, 0); cudaEventDestroy(b->last_use); }     // runs on other streams still read the batch
+    if (b->uploaded) cudaEventDestroy(b->uploaded);
     dfree(b->d_bad, st);
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
     dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->oz, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st); dfree(b->stitch_order, st);
+    dfree(b->rs_order, st);
     delete b;
     return SHB_OK;
 }
@@ -266,7 +299,7 @@ SHB_API int shb_batch_free(shb_batch* b) {
 SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
                      const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
                      const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_batch** out) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     if (!out) return fail(SHB_E_INVALID, "out is null");
     *out = nullptr;
@@ -287,7 +320,7 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     std::vector<uint32_t> item_off(n_sweep + 1, 0);
     std::vector<double> hs(G64), ho(heights, heights + G64), oz(G64);
     std::vector<uint32_t> pout(G64), pin(G64), psw(G64);
-    uint64_t prof = 0, items = 0;
+    uint64_t items = 0;
     std::vector<uint32_t> idx;
     for (int s = 0; s < n_sweep; ++s) {
         const int m = sweep_mesh[s];
@@ -296,13 +329,13 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
         if (P < 0) return fail(SHB_E_INVALID, "height offsets of sweep %d decrease", s);
         if (interp_num[s] < 2) return fail(SHB_E_INVALID, "interp_num of sweep %d must be >= 2", s);
         ShbSweep& sw = b->sweeps[s];
-        sw.z_orig = z_orig[s]; sw.prof_off = prof; sw.rad_off = 0;
+        sw = ShbSweep{};
+        sw.z_orig = z_orig[s];
         sw.plane_off = (uint32_t)p0; sw.n_plane = (uint32_t)P;
         sw.face_off = (uint32_t)face_off[m]; sw.n_face = (uint32_t)(face_off[m + 1] - face_off[m]);
         sw.item_off = (uint32_t)items; sw.interp_num = (uint32_t)interp_num[s]; sw.mesh = (uint32_t)m; sw.pad = 0;
         item_off[s] = (uint32_t)items;
         items += sw.n_face;
-        prof += (uint64_t)P * 2 * (uint64_t)interp_num[s];
         b->max_interp = std::max<uint32_t>(b->max_interp, (uint32_t)interp_num[s]);
         // planes ascending in height for the range search; linspace inputs are already monotone
         const double* h = heights + p0;
@@ -342,9 +375,10 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
         std::iota(order.begin(), order.end(), 0u);
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return endness[a] < endness[c]; });
     }
-    b->n_item = (uint32_t)items; b->prof_total = prof;
+    b->n_item = (uint32_t)items;
 
     cudaStream_t st = g.stream;
+    b->stream = st;
     const bool dbg = getenv("SHB_DEBUG_TIMING") != nullptr;
     auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
     double T0 = now();
@@ -379,78 +413,141 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st);
     // no host synchronisation here: the upload and K0 are only enqueued.  verts / faces must stay valid until the
     // first shb_batch_run on this batch returns (it synchronises); the face-index range check is reported there.
+    CK(cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming));
+    CK(cudaEventRecord(b->uploaded, st));
     if (dbg) fprintf(stderr, "[shb] create: alloc %.3f  h2d-enqueue %.3f  launch+free %.3f ms\n", T1 - T0, T2 - T1, now() - T2);
     *out = b.release();
     return SHB_OK;
 }
 
 SHB_API int shb_result_free(shb_result* r) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!r) return SHB_OK;
     if (r->pending) { cudaStreamSynchronize(g.copy); r->pending = false; }
-    cudaStream_t st = g.stream;
+    cudaStream_t st = r->stream ? r->stream : g.stream;      // the stream that computed it: frees are ordered behind its kernels
     ShbDev& d = r->d;
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
     dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.cap_sorted, st); dfree(d.totals, st); dfree(d.totals64, st);
     dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
     dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
     dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
-    dfree(d.ct_start, st); dfree(d.ct_len, st); dfree(d.ct_area, st);
+    dfree(d.ct_start, st); dfree(d.ct_len, st); dfree(d.ct_area, st); dfree(d.decl_list, st); dfree(d.dup_list, st);
     for (int a = 0; a < 6; ++a) if (d.prof[a]) { cudaFreeAsync(d.prof[a], st); d.prof[a] = nullptr; }
     if (d.radial) { cudaFreeAsync(d.radial, st); d.radial = nullptr; }
     dfree(d.scratch, st);
     if (d.sweep) { cudaFreeAsync(const_cast<ShbSweep*>(d.sweep), st); d.sweep = nullptr; }
     dfree(r->d_ct_off, st); dfree(r->d_pt_off, st); dfree(r->d_pts_c, st); dfree(r->d_ctpt_c, st); dfree(r->d_ctarea_c, st);
     void* hp[] = {r->h_nseg, r->h_nent, r->h_sel, r->h_face_index, r->h_status, r->h_seg_off, r->h_ct_off, r->h_pt_off,
-                  r->h_bounds, r->h_centroid, r->h_area1, r->h_segments, r->h_pts, r->h_ctarea, r->h_ctpt, r->h_radial,
-                  r->h_prof[0], r->h_prof[1], r->h_prof[2], r->h_prof[3], r->h_prof[4], r->h_prof[5]};
+                  r->h_bounds, r->h_centroid, r->h_area1, r->h_segments, r->h_pts, r->h_ctarea, r->h_ctpt,
+                  r->h_arr[0], r->h_arr[1], r->h_arr[2], r->h_arr[3], r->h_arr[4], r->h_arr[5], r->h_arr[6]};
     for (void* p : hp) if (p) pinned_put(p);
     if (r->done) cudaEventDestroy(r->done);
     delete r;
     return SHB_OK;
 }
 
+static const uint32_t kArrBit[SHB_N_ARR] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
+                                            SHB_OUT_ITR_CENTERED_START, SHB_OUT_RADIAL};
+
 SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles, shb_result** out) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    return shb_batch_run_req(b, nullptr, outputs_mask, n_angles, out);
+}
+
+SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32_t outputs_mask, int32_t n_angles, shb_result** out) {
+    SHB_ENTER;
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     if (!b || !out) return fail(SHB_E_INVALID, "null batch/out");
     *out = nullptr;
     outputs_mask |= SHB_OUT_PLANE;
-    if ((outputs_mask & SHB_OUT_RADIAL) && n_angles < 1) return fail(SHB_E_INVALID, "n_angles must be >= 1 for the radial image");
-    if (!(outputs_mask & SHB_OUT_RADIAL)) n_angles = 0;
     cudaStream_t st = g.stream;
     const uint32_t G = b->G;
     struct ResultDel { void operator()(shb_result* p) const { shb_result_free(p); } };
     std::unique_ptr<shb_result, ResultDel> r(new shb_result);
-    r->batch = b; r->sweeps = b->sweeps; r->G = G; r->mask = outputs_mask; r->n_angles = (uint32_t)n_angles;
-    r->prof_total = b->prof_total; r->rel.resize((size_t)b->n_sweep * 3);
+    r->batch = b; r->sweeps = b->sweeps; r->G = G; r->stream = st;
+    r->rel.resize((size_t)b->n_sweep * 3);
     r->esz = (outputs_mask & SHB_OUT_F32) ? 4 : 8;
-    uint64_t rad = 0;
-    for (auto& sw : r->sweeps) { sw.rad_off = rad; rad += (uint64_t)sw.n_plane * (uint64_t)n_angles; }
-    r->rad_total = rad;
+    // ---- per-sweep requests: which windowed arrays, over which rows (slice.py:157-164 windows of the consumers)
+    uint32_t any_mask = 0;
+    uint64_t excluded = 0, key = 1469598103934665603ull;          // FNV over the request: identifies the cached launch list
+    for (int s = 0; s < b->n_sweep; ++s) {
+        ShbSweep& sw = r->sweeps[s];
+        const uint32_t m = req ? req[s].outputs_mask : outputs_mask;
+        uint32_t lo_any = sw.n_plane, hi_any = 0;
+        for (int a = 0; a < SHB_N_ARR; ++a) {
+            uint32_t lo = 0, hi = 0;
+            if (m & kArrBit[a]) {
+                int64_t l = req ? req[s].row_lo[a] : 0, h = req ? req[s].row_hi[a] : -1;
+                if (h < 0) h = sw.n_plane;
+                if (l < 0 || l > h || h > (int64_t)sw.n_plane)
+                    return fail(SHB_E_INVALID, "sweep %d: window [%lld, %lld) of array %d is outside its %u planes", s, (long long)l, (long long)h, a, sw.n_plane);
+                lo = (uint32_t)l; hi = (uint32_t)h;
+            }
+            sw.win_lo[a] = lo; sw.win_hi[a] = hi;
+            const uint64_t per = a == SHB_A_RADIAL ? (uint64_t)std::max(n_angles, 0) : 2ull * sw.interp_num;
+            sw.arr_off[a] = r->arr_total[a];
+            r->arr_total[a] += (uint64_t)(hi - lo) * per;
+            if (hi > lo) { any_mask |= kArrBit[a]; lo_any = std::min(lo_any, lo); hi_any = std::max(hi_any, hi); }
+            key = (key ^ (((uint64_t)lo << 32) | hi)) * 1099511628211ull;
+        }
+        excluded += hi_any > lo_any ? sw.n_plane - (hi_any - lo_any) : sw.n_plane;
+    }
+    if ((any_mask & SHB_OUT_RADIAL) && n_angles < 1) return fail(SHB_E_INVALID, "n_angles must be >= 1 for the radial image");
+    if (!(any_mask & SHB_OUT_RADIAL)) n_angles = 0;
+    outputs_mask = (outputs_mask & ~(SHB_OUT_ALL_PROFILES | SHB_OUT_RADIAL)) | any_mask;
+    r->mask = outputs_mask; r->n_angles = (uint32_t)n_angles;
     ShbDev& d = r->d;
     d.vert = b->vert; d.vz = b->vz; d.face = b->face; d.item_off = b->d_item_off;
     d.h_sorted = b->h_sorted; d.h_orig = b->h_orig; d.oz = b->oz; d.plane_out = b->plane_out; d.plane_in = b->plane_in; d.plane_sweep = b->plane_sweep;
     d.n_sweep = (uint32_t)b->n_sweep; d.n_plane = G; d.n_item = b->n_item;
     d.n_angles = (uint32_t)n_angles; d.outputs_mask = outputs_mask;
-    // sweep descriptors carry the radial offsets of this run
+    if (b->stream != st && b->uploaded) CK(cudaStreamWaitEvent(st, b->uploaded, 0));     // the batch was uploaded on another stream
+    // sweep descriptors carry the windows and output offsets of this run
     ShbSweep* d_sw = nullptr;
     CK(dalloc(&d_sw, b->n_sweep, st));
     Staging stage;
+    struct StageSync { Staging& s; cudaStream_t st; bool armed = true;      // an early return must not hand the pinned buffers back
+        ~StageSync() { if (armed && !s.bufs.empty()) { cudaStreamSynchronize(st); s.release(); } } } stage_sync{stage, st};
     CK(stage.copy(d_sw, r->sweeps.data(), b->n_sweep * sizeof(ShbSweep), st));
     d.sweep = d_sw;
+    // launch list of the resample kernel: only the planes some windowed output wants (built once per request)
+    d.resample_order = nullptr; d.n_resample = 0;
+    if (excluded && any_mask) {
+        if (b->rs_key != key || !b->rs_order) {
+            std::vector<uint32_t> so(G), list;
+            // the host copy of the stitch order is not kept: rebuild "sweep ends first" for the wanted planes only
+            std::vector<std::pair<double, uint32_t>> cand;
+            for (int s = 0; s < b->n_sweep; ++s) {
+                const ShbSweep& sw = r->sweeps[s];
+                for (uint32_t lp = 0; lp < sw.n_plane; ++lp) {
+                    bool want = false;
+                    for (int a = 0; a < SHB_N_ARR; ++a) want |= lp >= sw.win_lo[a] && lp < sw.win_hi[a];
+                    if (!want) continue;
+                    const uint32_t e = std::min(lp, sw.n_plane - 1 - lp);
+                    cand.push_back({(double)e / (double)std::max<uint32_t>(sw.n_plane, 1u), sw.plane_off + lp});
+                }
+            }
+            std::stable_sort(cand.begin(), cand.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+            list.reserve(cand.size());
+            for (auto& c : cand) list.push_back(c.second);
+            if (b->rs_order) dfree(b->rs_order, b->stream);
+            CK(dalloc(&b->rs_order, list.size(), st));
+            CK(stage.copy(b->rs_order, list.data(), list.size() * sizeof(uint32_t), st));
+            b->n_rs = (uint32_t)list.size(); b->rs_key = key;
+        }
+        d.resample_order = b->rs_order; d.n_resample = b->n_rs;
+    }
 
     CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
     CK(dalloc(&d.inc, G, st)); CK(dalloc(&d.sort_off, G + 1, st)); CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cnt, G, st));
     const size_t n_tiles = ((size_t)G + 4095) / 4096;
     CK(dalloc(&d.scan_state, 4 * n_tiles + 4, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st)); CK(dalloc(&d.cap_sorted, G, st));
-    CK(dalloc(&d.totals, 8, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
+    CK(dalloc(&d.totals, 16, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
     CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
     CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
-    CK(dalloc(&d.o_sel, 2 * (size_t)G, st));
+    CK(dalloc(&d.o_sel, 2 * (size_t)G, st)); CK(dalloc(&d.decl_list, G, st)); CK(dalloc(&d.dup_list, G, st));
     CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, ((size_t)G + 1) * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(d.totals, 0, 8 * sizeof(uint32_t), st));
+    CK(cudaMemsetAsync(d.totals, 0, 16 * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.scan_state, 0, (4 * n_tiles + 4) * sizeof(unsigned long long), st));
     CK(cudaMemcpyAsync(d.totals + SHB_T_BAD, b->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));   // slot 1: bad-face flag
 
@@ -470,16 +567,19 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     }
     cap = d.stitch_cap; pcap = d.resample_cap;
     d.debug = 0;
+    if (getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= 1u;       // radius image by the all-candidates path on every plane
+    if (getenv("SHB_DEBUG_MINRANK_ORDER")) d.debug |= 2u;        // contour order by minimum rank (no CPython-set emulation)
+    if (getenv("SHB_DEBUG_NO_WARP_STITCH")) d.debug |= 4u;       // every plane through the CTA stitcher
     d.stitch_order = getenv("SHB_DEBUG_NO_PERMUTE") ? nullptr : b->stitch_order;
     // K1 sizes everything downstream: the candidate triangles per plane (an upper bound of the hits that is exact
     // except on planes through vertices) are published as soon as the bucket histograms are scanned, and the host
     // waits for them while the device goes on with the counting sort
-    { StageTimer t(0); t.stop(shb_launch_bucket(d, st)); }
-    { StageTimer t(1); t.stop(shb_launch_scan_candidates(d, st)); }
+    { StageTimer t(0, st); t.stop(shb_launch_bucket(d, st)); }
+    { StageTimer t(1, st); t.stop(shb_launch_scan_candidates(d, st)); }
     g.launches += shb_launch_publish(d.totals, 8, d.totals64, g.h_totals, g.h_totals64, st);
     CK(cudaEventRecord(g.sized, st));
-    { StageTimer t(1); t.stop(shb_launch_scan_planes(d, st)); }
-    { StageTimer t(2); t.stop(shb_launch_scatter(d, st)); }
+    { StageTimer t(1, st); t.stop(shb_launch_scan_planes(d, st)); }
+    { StageTimer t(2, st); t.stop(shb_launch_scatter(d, st)); }
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st));      // reused as the hit-list cursors
     const bool dbg_t = getenv("SHB_DEBUG_TIMING") != nullptr;
     auto now_ms = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
@@ -487,28 +587,27 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
     CK(cudaEventSynchronize(g.sized));      // the one host wait of a run
     const double tw1 = now_ms();
     stage.release();
-    if (b->stage) { delete b->stage; b->stage = nullptr; }      // the batch upload has executed too
+    if (b->stage && b->stream == st) { delete b->stage; b->stage = nullptr; }      // the batch upload has executed too
     if (g.h_totals[SHB_T_BAD]) return fail(SHB_E_INVALID, "face index out of range for its mesh");
     const uint32_t S = g.h_totals[SHB_T_CAP], maxcand = g.h_totals[SHB_T_MAXN];      // S: capacity (candidates), >= segments
     if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu candidate segments in one batch; split it", g.h_totals64[0]);
     r->W = S;
     const uint32_t avgn = (uint32_t)(S / std::max<uint32_t>(G, 1u));     // mean segments per plane picks the CTA size
     CK(dalloc(&d.hits, (size_t)S + 1, st));      // 16-byte records: every plane's list is a TMA-aligned run
-    CK(dalloc(&d.face_index, S, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
+    const bool want_seg = (outputs_mask & SHB_OUT_SEGMENTS) != 0;
+    CK(dalloc(&d.face_index, want_seg ? S : 1, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
     CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
-    const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
-                              SHB_OUT_ITR_CENTERED_START};
     bool any_prof = false;
     for (int a = 0; a < 6; ++a)
-        if (outputs_mask & pbit[a]) { CK(cudaMallocAsync(&d.prof[a], std::max<size_t>(r->prof_total, 1) * r->esz, st)); any_prof = true; }
-    if (outputs_mask & SHB_OUT_RADIAL) {
-        CK(cudaMallocAsync(&d.radial, std::max<size_t>(r->rad_total, 1) * r->esz, st)); any_prof = true;
+        if (r->arr_total[a]) { CK(dalloc_bytes(&d.prof[a], r->arr_total[a] * r->esz, st)); any_prof = true; }
+    if (r->arr_total[SHB_A_RADIAL]) {
+        CK(dalloc_bytes(&d.radial, r->arr_total[SHB_A_RADIAL] * r->esz, st)); any_prof = true;
         // ray directions from the host's libm (what numpy evaluates): theta_k = -pi + (2*pi/A)*k; cached per A
         if (g.angle_n != n_angles) {
             std::vector<double> tab(2 * (size_t)n_angles);
             const double pi = 3.141592653589793, dA = 2.0 * pi / (double)n_angles;
             for (int k = 0; k < n_angles; ++k) { double th = -pi + dA * (double)k; tab[2 * k] = std::cos(th); tab[2 * k + 1] = std::sin(th); }
-            if (g.angle_tab) cudaFree(g.angle_tab);
+            if (g.angle_tab) { CK(cudaDeviceSynchronize()); cudaFree(g.angle_tab); g.angle_tab = nullptr; }
             CK(cudaMalloc(&g.angle_tab, (size_t)n_angles * sizeof(double2)));
             CK(cudaMemcpy(g.angle_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
             g.angle_n = n_angles;
@@ -522,18 +621,22 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
         CK(dalloc(&d.scratch, d.scratch_stride * (size_t)g.n_sm, st));
     }
 
-    { StageTimer t(3); t.stop(shb_launch_intersect(d, st)); }
-    { StageTimer t(4); t.stop(shb_launch_scan_counts(d, st)); }
-    { StageTimer t(5); t.stop(shb_launch_stitch(d, maxcand, avgn, g.n_sm, st)); }
-    if (any_prof) { StageTimer t(6); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
+    { StageTimer t(3, st); t.stop(shb_launch_intersect(d, st)); }
+    { StageTimer t(4, st); t.stop(shb_launch_scan_counts(d, st)); }
+    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, g.n_sm, st)); }
+    if (any_prof) { StageTimer t(6, st); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
     dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
-    dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st);
+    dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st); dfree(d.decl_list, st); dfree(d.dup_list, st);
     dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.cap_sorted, st); dfree(d.scratch, st);
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
+    d.resample_order = nullptr;
     CK(cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming));
     CK(cudaEventRecord(r->done, st));
+    if (!b->last_use) CK(cudaEventCreateWithFlags(&b->last_use, cudaEventDisableTiming));
+    CK(cudaEventRecord(b->last_use, st));
+    stage_sync.armed = false;
     if (dbg_t) fprintf(stderr, "[shb] run: host waited %.3f ms for the sizes, then enqueued the rest in %.3f ms\n", tw1 - tw0, now_ms() - tw1);
     *out = r.release();
     return SHB_OK;
@@ -571,21 +674,21 @@ static int finish_fetch(shb_result* r) {
 static int enqueue_fetch(shb_result* r, uint32_t mask);
 
 SHB_API int shb_result_fetch(shb_result* r, uint32_t mask) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!r) return fail(SHB_E_INVALID, "null result");
     int rc = enqueue_fetch(r, mask);
     return rc ? rc : finish_fetch(r);
 }
 
 SHB_API int shb_result_fetch_async(shb_result* r, uint32_t mask) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!r) return fail(SHB_E_INVALID, "null result");
     if (mask & SHB_OUT_CONTOURS) return fail(SHB_E_INVALID, "contours need a size readback; fetch them with shb_result_fetch");
     return enqueue_fetch(r, mask);
 }
 
 static int enqueue_fetch(shb_result* r, uint32_t mask) {
-    cudaStream_t st = g.copy, cst = g.stream;
+    cudaStream_t st = g.copy, cst = r->stream ? r->stream : g.stream;
     int rc = fetch_plane(r);
     if (rc) return rc;
     if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
@@ -623,28 +726,23 @@ static int enqueue_fetch(shb_result* r, uint32_t mask) {
         CK(cudaMemcpyAsync(r->h_ctarea, r->d_ctarea_c, (size_t)r->n_cont * 8, cudaMemcpyDeviceToHost, st));
         r->have_cont = true; r->pending = true;
     }
-    const uint32_t pbit[6] = {SHB_OUT_IXY, SHB_OUT_IXY_CENTERED, SHB_OUT_ITR, SHB_OUT_ITR_START, SHB_OUT_ITR_CENTERED,
-                              SHB_OUT_ITR_CENTERED_START};
-    for (int a = 0; a < 6; ++a)
-        if ((mask & pbit[a]) && !r->h_prof[a]) {
-            if (!r->d.prof[a]) return fail(SHB_E_STATE, "profile array %d was not in the outputs_mask of the run", a);
-            r->h_prof[a] = pinned_get(r->prof_total * r->esz);
-            if (!r->h_prof[a]) return fail(SHB_E_NOMEM, "pinned host allocation failed");
-            CK(cudaMemcpyAsync(r->h_prof[a], r->d.prof[a], r->prof_total * r->esz, cudaMemcpyDeviceToHost, st));
+    for (int a = 0; a < SHB_N_ARR; ++a)
+        if ((mask & kArrBit[a]) && !r->h_arr[a]) {
+            void* src = a == SHB_A_RADIAL ? r->d.radial : r->d.prof[a];
+            if (!src) {
+                if (mask & r->mask & kArrBit[a]) continue;              // requested, but no sweep window held a row
+                return fail(SHB_E_STATE, "output array %d was not in the outputs_mask of the run", a);
+            }
+            r->h_arr[a] = pinned_get(r->arr_total[a] * r->esz);
+            if (!r->h_arr[a]) return fail(SHB_E_NOMEM, "pinned host allocation failed");
+            CK(cudaMemcpyAsync(r->h_arr[a], src, r->arr_total[a] * r->esz, cudaMemcpyDeviceToHost, st));
             r->pending = true;
         }
-    if ((mask & SHB_OUT_RADIAL) && !r->h_radial) {
-        if (!r->d.radial) return fail(SHB_E_STATE, "radial image was not in the outputs_mask of the run");
-        r->h_radial = pinned_get(r->rad_total * r->esz);
-        if (!r->h_radial) return fail(SHB_E_NOMEM, "pinned host allocation failed");
-        CK(cudaMemcpyAsync(r->h_radial, r->d.radial, r->rad_total * r->esz, cudaMemcpyDeviceToHost, st));
-        r->pending = true;
-    }
     return SHB_OK;
 }
 
 SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n_seg, int64_t* n_contour, int64_t* n_point) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     shb_result* r = const_cast<shb_result*>(r_);
     if (!r) return fail(SHB_E_INVALID, "null result");
     int rc = fetch_plane(r);
@@ -663,7 +761,7 @@ SHB_API int shb_result_totals(const shb_result* r_, int64_t* n_plane, int64_t* n
 }
 
 SHB_API const void* shb_result_array(shb_result* r, int32_t which, int32_t sweep, int64_t shape[4], int32_t* ndim, int32_t* dtype) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     if (!r || !shape || !ndim || !dtype) { fail(SHB_E_INVALID, "null argument"); return nullptr; }
     if (sweep < 0 || sweep >= (int32_t)r->sweeps.size()) { fail(SHB_E_INVALID, "sweep %d out of range", sweep); return nullptr; }
     uint32_t need = SHB_OUT_PLANE;
@@ -720,20 +818,34 @@ SHB_API const void* shb_result_array(shb_result* r, int32_t which, int32_t sweep
         case SHB_ARR_POINTS: *dtype = SHB_DT_F64; *ndim = 2; shape[0] = (int64_t)r->h_pt_off[p0 + P] - r->h_pt_off[p0]; shape[1] = 2;
             return r->h_pts + 2 * (size_t)r->h_pt_off[p0];
         case SHB_ARR_RADIAL: *dtype = r->esz == 4 ? SHB_DT_F32 : SHB_DT_F64; *ndim = 2; shape[1] = r->n_angles;
-            return (const char*)r->h_radial + sw.rad_off * r->esz;
+            shape[0] = (int64_t)sw.win_hi[SHB_A_RADIAL] - sw.win_lo[SHB_A_RADIAL];         // the rows of the sweep's window
+            if (shape[0] == 0 && !r->h_arr[SHB_A_RADIAL]) { fail(SHB_E_STATE, "sweep %d did not request the radial image", sweep); return nullptr; }
+            return (const char*)r->h_arr[SHB_A_RADIAL] + sw.arr_off[SHB_A_RADIAL] * r->esz;
         default: {
             const int a = which - SHB_ARR_IXY;
             *dtype = r->esz == 4 ? SHB_DT_F32 : SHB_DT_F64; *ndim = 3; shape[1] = 2; shape[2] = (int64_t)N;
-            return (const char*)r->h_prof[a] + sw.prof_off * r->esz;
+            shape[0] = (int64_t)sw.win_hi[a] - sw.win_lo[a];
+            if (shape[0] == 0 && !r->h_arr[a]) { fail(SHB_E_STATE, "sweep %d did not request profile array %d", sweep, a); return nullptr; }
+            return (const char*)r->h_arr[a] + sw.arr_off[a] * r->esz;
         }
     }
+}
+
+SHB_API int shb_result_window(const shb_result* r, int32_t which, int32_t sweep, int32_t* row_lo, int32_t* row_hi) {
+    SHB_ENTER;
+    if (!r || sweep < 0 || sweep >= (int32_t)r->sweeps.size()) return fail(SHB_E_INVALID, "bad result / sweep");
+    const int a = which == SHB_ARR_RADIAL ? SHB_A_RADIAL : which - SHB_ARR_IXY;
+    if (a < 0 || a >= SHB_N_ARR) return fail(SHB_E_INVALID, "array %d has no row window", which);
+    if (row_lo) *row_lo = (int32_t)r->sweeps[sweep].win_lo[a];
+    if (row_hi) *row_hi = (int32_t)r->sweeps[sweep].win_hi[a];
+    return SHB_OK;
 }
 
 SHB_API int shb_sweep_batch(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
                     const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
                     const double* heights, const int64_t* height_off, const int32_t* interp_num, uint32_t outputs_mask,
                     int32_t n_angles, shb_result** out) {
-    std::lock_guard<std::recursive_mutex> lk(g.mu);
+    SHB_ENTER;
     shb_batch* b = nullptr;
     int rc = shb_batch_create(n_mesh, verts, vert_off, faces, face_off, n_sweep, sweep_mesh, z_orig, heights, height_off, interp_num, &b);
     if (rc) return rc;

@@ -8,10 +8,13 @@
 #define SHB_HIT_FACE   0x1FFFFFFFu   // face bits of a hit record's x word
 
 // sweep descriptor, one per (mesh, height list) pair — device resident
+#define SHB_N_ARR 7          // windowed per-plane outputs of the resample kernel: the six profile arrays + the radius image
+#define SHB_A_RADIAL 6
 struct ShbSweep {
     double   z_orig;      // plane origin z (slice.py:18)
-    uint64_t prof_off;    // offset in doubles of this sweep's (P,2,N) block in every profile array
-    uint64_t rad_off;     // offset in doubles of this sweep's (P,A) block in the radial image
+    uint64_t arr_off[SHB_N_ARR];   // element offset of this sweep's block in output array a: (rows,2,N) profiles, (rows,A) radius image
+    uint32_t win_lo[SHB_N_ARR];    // rows [win_lo, win_hi) of the sweep are computed and delivered for array a (the consumers'
+    uint32_t win_hi[SHB_N_ARR];    // _cutoff windows, slice.py:157-164); lo == hi: the sweep does not ask for array a
     uint32_t plane_off;   // first global plane index
     uint32_t n_plane;
     uint32_t face_off;    // first global face index of the sweep's mesh
@@ -38,9 +41,8 @@ struct ShbPlaneMeta {
     // what the resample kernel needs of the plane's sweep, so that it starts from ONE record instead of the
     // plane -> sorted plane -> sweep -> descriptor chain of dependent loads
     uint32_t interp_num;  // N of the plane's sweep
-    uint32_t pad;
-    uint64_t prof_row;    // element offset of the plane's (2, N) block in every profile array
-    uint64_t rad_row;     // element offset of the plane's A rays in the radius image
+    uint32_t arr_mask;    // bit a: output array a is wanted for this plane (requested by its sweep and inside the window)
+    uint64_t arr_row[SHB_N_ARR];   // element offset of the plane's (2, N) block in profile array a / of its A rays in the radius image
     uint64_t sel_pt;      // index (in points) of the outline's first point in ShbDev::pts
 };
 
@@ -58,6 +60,8 @@ struct ShbDev {
     const uint32_t* plane_in;    // [G] original global plane -> sorted plane
     const uint32_t* plane_sweep; // [G] sweep of sorted plane
     const uint32_t* stitch_order;// [G] CTA b of the stitch launch takes plane stitch_order[b]: sweep ends first (nullptr: identity)
+    const uint32_t* resample_order; // [n_resample] planes the resample launch covers (nullptr: stitch_order, all planes)
+    uint32_t n_resample;
     uint32_t n_sweep, n_plane /*G*/, n_item;
     // ---- per-run scratch
     uint32_t* item_lo;    // [n_item] first sorted plane of the triangle's range
@@ -70,13 +74,17 @@ struct ShbDev {
     uint32_t* cap_off;    // [G+1] hit-list offsets by candidate capacity, original plane order
     uint32_t* cap_sorted; // [G]   the same offsets indexed by sorted plane (what the intersect kernel has at hand)
     unsigned long long* scan_state;   // [4][ceil(G/4096)] tile aggregates of the four scans of a run + 4 tile tickets, zeroed per run
-    uint32_t* totals;     // [8]   M, -, -, S, maxn, nbig, ...
+    uint32_t* totals;     // [16]  M, bad, cap, S, maxn, nbig, ncont, npts, ndecl, ndup
     uint4*    rec;        // [n_item] bucketed triangles (face, lo, span, sweep); first M are live
     uint4*    hits;       // [S]   per-plane hit records, caller plane order: x = global face id | tag << 29 | (lone vertex above) << 31,
                           //       y, z, w = lone vertex u and the two others in cyclic order (basic crossings, tag = position of u);
                           //       tag 3 = a vertex on the plane (the stitcher classifies such faces itself)
     uint32_t* seg_off;    // [G+1] exact segment offsets, original plane order
     uint32_t* big_list;   // [G]   planes too large for shared memory
+    uint32_t* decl_list;  // [G]   planes the warp stitcher declined (several contours, on-plane vertices, open / non-manifold
+                          //       nodes, inconsistent winding, too large): the CTA stitcher takes them; count in totals[SHB_T_NDECL]
+    uint32_t* dup_list;   // [G]   planes with two consecutive contour nodes closer than Path.merge_vertices' grid: the
+                          //       merge pass takes them; count in totals[SHB_T_NDUP]
     // ---- outputs (device)
     ShbPlaneMeta* meta;   // [G]  (kernel-internal AoS; the arrays below are what the host reads)
     int32_t*  o_nseg;     // [G]
@@ -106,7 +114,7 @@ struct ShbDev {
 };
 
 enum { SHB_T_M = 0, SHB_T_BAD = 1, SHB_T_CAP = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
-       SHB_T_NCONT = 6, SHB_T_NPTS = 7 };
+       SHB_T_NCONT = 6, SHB_T_NPTS = 7, SHB_T_NDECL = 8, SHB_T_NDUP = 9 };
 
 // bytes of workspace the stitch kernel needs for a plane with n segments
 __host__ __device__ inline uint32_t shb_pow2_ge(uint32_t x) {
