@@ -146,7 +146,8 @@ struct StageTimer {
 struct shb_batch {
     int32_t n_mesh = 0, n_sweep = 0;
     int64_t n_vert = 0, n_face = 0;
-    uint32_t G = 0, n_item = 0, max_interp = 0;
+    uint32_t G = 0, n_item = 0, max_interp = 0, max_faces = 0;
+    uint32_t* adj = nullptr;               // [T][4] face adjacency (built once per batch by K0b)
     std::vector<ShbSweep> sweeps;          // host copy
     double4* vert = nullptr; double* vz = nullptr; int4* face = nullptr;
     ShbSweep* d_sweep = nullptr; uint32_t* d_item_off = nullptr;
@@ -289,6 +290,7 @@ SHB_API int shb_batch_free(shb_batch* b) {
     if (b->last_use) { cudaStreamWaitEvent(st, b->last_use, 0); cudaEventDestroy(b->last_use); }     // runs on other streams still read the batch
     if (b->uploaded) cudaEventDestroy(b->uploaded);
     dfree(b->d_bad, st);
+    dfree(b->adj, st);
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
     dfree(b->h_sorted, st); dfree(b->h_orig, st); dfree(b->oz, st); dfree(b->plane_out, st); dfree(b->plane_in, st); dfree(b->plane_sweep, st); dfree(b->stitch_order, st);
     dfree(b->rs_order, st);
@@ -411,6 +413,21 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, b->d_bad, st);
     CK(cudaGetLastError());
     dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st);
+    {   // K0b: face adjacency of the batch (one hash table over its undirected edges; temporary)
+        for (int m = 0; m < n_mesh; ++m) b->max_faces = std::max<uint32_t>(b->max_faces, (uint32_t)(face_off[m + 1] - face_off[m]));
+        CK(dalloc(&b->adj, 4 * (size_t)std::max<int64_t>(nf, 1), st));
+        if (nf) {
+            uint32_t hs = 1024;
+            while ((uint64_t)hs < 3ull * (uint64_t)nf) hs <<= 1;              // 1.5 T edges -> load <= 0.5
+            unsigned long long* keys = nullptr; uint32_t *cnt = nullptr, *own = nullptr, *hslot = nullptr;
+            CK(dalloc(&keys, hs, st)); CK(dalloc(&cnt, hs, st)); CK(dalloc(&own, 2 * (size_t)hs, st)); CK(dalloc(&hslot, 3 * (size_t)nf, st));
+            CK(cudaMemsetAsync(keys, 0xFF, (size_t)hs * sizeof(unsigned long long), st));
+            CK(cudaMemsetAsync(cnt, 0, (size_t)hs * sizeof(uint32_t), st));
+            g.launches += shb_launch_adjacency(b->face, nf, keys, cnt, own, hslot, hs, b->adj, st);
+            CK(cudaGetLastError());
+            dfree(keys, st); dfree(cnt, st); dfree(own, st); dfree(hslot, st);
+        }
+    }
     // no host synchronisation here: the upload and K0 are only enqueued.  verts / faces must stay valid until the
     // first shb_batch_run on this batch returns (it synchronises); the face-index range check is reported there.
     CK(cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming));
@@ -496,7 +513,7 @@ SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32
     outputs_mask = (outputs_mask & ~(SHB_OUT_ALL_PROFILES | SHB_OUT_RADIAL)) | any_mask;
     r->mask = outputs_mask; r->n_angles = (uint32_t)n_angles;
     ShbDev& d = r->d;
-    d.vert = b->vert; d.vz = b->vz; d.face = b->face; d.item_off = b->d_item_off;
+    d.vert = b->vert; d.vz = b->vz; d.face = b->face; d.adj = b->adj; d.item_off = b->d_item_off;
     d.h_sorted = b->h_sorted; d.h_orig = b->h_orig; d.oz = b->oz; d.plane_out = b->plane_out; d.plane_in = b->plane_in; d.plane_sweep = b->plane_sweep;
     d.n_sweep = (uint32_t)b->n_sweep; d.n_plane = G; d.n_item = b->n_item;
     d.n_angles = (uint32_t)n_angles; d.outputs_mask = outputs_mask;
@@ -623,7 +640,7 @@ SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32
 
     { StageTimer t(3, st); t.stop(shb_launch_intersect(d, st)); }
     { StageTimer t(4, st); t.stop(shb_launch_scan_counts(d, st)); }
-    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, g.n_sm, st)); }
+    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, b->max_faces, budget, g.n_sm, st)); }
     if (any_prof) { StageTimer t(6, st); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)

@@ -51,6 +51,7 @@ struct ShbDev {
     const double4*  vert;        // (x, y, z, 0) per global vertex
     const double*   vz;          // z only (dense, for the bucket / intersect kernels)
     const int4*     face;        // global vertex ids (a, b, c, 0) per global face
+    const uint32_t* adj;         // [T][4] global ids of the faces across edges (v0 v1), (v1 v2), (v2 v0); SHB_NIL = none
     const ShbSweep* sweep;
     const uint32_t* item_off;    // [n_sweep+1] prefix of faces per sweep
     const double*   h_sorted;    // [G] heights ascending within each sweep
@@ -76,8 +77,9 @@ struct ShbDev {
     unsigned long long* scan_state;   // [4][ceil(G/4096)] tile aggregates of the four scans of a run + 4 tile tickets, zeroed per run
     uint32_t* totals;     // [16]  M, bad, cap, S, maxn, nbig, ncont, npts, ndecl, ndup
     uint4*    rec;        // [n_item] bucketed triangles (face, lo, span, sweep); first M are live
-    uint4*    hits;       // [S]   per-plane hit records, caller plane order: x = global face id | tag << 29 | (lone vertex above) << 31,
-                          //       y, z, w = lone vertex u and the two others in cyclic order (basic crossings, tag = position of u);
+    uint4*    hits;       // [S]   per-plane hit records, caller plane order: x = mesh-local face id | tag << 29 | (lone vertex above) << 31,
+                          //       basic crossings (tag = position of the lone vertex u): y = mesh-local id of the face the contour
+                          //       continues in (across the END edge), z = u, w = the other vertex of the END edge;
                           //       tag 3 = a vertex on the plane (the stitcher classifies such faces itself)
     uint32_t* seg_off;    // [G+1] exact segment offsets, original plane order
     uint32_t* big_list;   // [G]   planes too large for shared memory
@@ -176,13 +178,15 @@ extern "C" {
 int shb_launch_prep_mesh(const double* verts_in, const int64_t* faces_in, const int64_t* vert_off,
                          const int64_t* face_off, int n_mesh, int64_t n_vert, int64_t n_face,
                          double4* vert, double* vz, int4* face, uint32_t* bad, cudaStream_t st);
+int shb_launch_adjacency(const int4* face, int64_t n_face, unsigned long long* keys, uint32_t* cnt, uint32_t* own, uint32_t* hslot,
+                         uint32_t hsize, uint32_t* adj, cudaStream_t st);
 int shb_launch_bucket(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_planes(const ShbDev& d, cudaStream_t st);
 int shb_launch_scatter(const ShbDev& d, cudaStream_t st);
 int shb_launch_intersect(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_candidates(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
-int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, int n_sm, cudaStream_t st);
+int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t max_faces, size_t smem_budget, int n_sm, cudaStream_t st);
 int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t maxN, int n_sm, cudaStream_t st);
 int shb_launch_compact(const ShbDev& d, const uint32_t* ct_off, const uint32_t* pt_off,
                        double* pts_out, int64_t* ctpt_out, double* ctarea_out, cudaStream_t st);

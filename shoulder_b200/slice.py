@@ -12,6 +12,13 @@ names, argument meaning, windowing (:157-164) and quirks:
 Everything numeric comes from one call into ``libshoulder_b200.so`` per object (or per batch of
 objects, see :func:`run_batch`); arrays are fetched from the device lazily, on first access, the
 way the reference memoises with ``cached_property``.  There is no CPU path.
+
+What a provider asks the device for is what the reference's consumers read (``consumer_windows``): the Full sweep
+feeds ``canal.py:40-46`` (centroids) and ``surgical_neck.py:31-34`` (areas) — plane records only; the Distal sweep
+feeds ``epicondyle.py:33-43`` (37 polygons) — plane records + contours on demand; the Proximal sweep feeds
+``anatomic_neck.py:34-36`` (``itr_start((0, 0.852))``: rows 88..599 of 600) and ``bicipital_groove.py:161-162``
+(``itr_centered_start((0.2, 0.75))``: rows 150..479).  Only those rows are computed and cross PCIe.  Any other array or
+window is still served, by a second run on first access, so the accessor set behaves like the reference's.
 """
 from __future__ import annotations
 
@@ -30,7 +37,9 @@ _PROFILE_ARRAYS = {
     "_itr_centered": _lib.ARR_ITR_CENTERED,
     "_itr_centered_start": _lib.ARR_ITR_CENTERED_START,
 }
-_RUN_MASK = _lib.OUT_PLANE | _lib.OUT_ALL_PROFILES
+_RUN_MASK = _lib.OUT_PLANE
+_OUT_BIT = {"_ixy": _lib.OUT_IXY, "_ixy_centered": _lib.OUT_IXY_CENTERED, "_itr": _lib.OUT_ITR, "_itr_start": _lib.OUT_ITR_START,
+            "_itr_centered": _lib.OUT_ITR_CENTERED, "_itr_centered_start": _lib.OUT_ITR_CENTERED_START}
 
 
 class GpuSlices:
@@ -40,9 +49,24 @@ class GpuSlices:
     #: the device, rounded on store) halves the device->host bytes and stays inside north_star's 1e-5 budget.
     profile_dtype = np.float64
 
+    #: cached array -> fractional window its consumer reads (slice.py:157-164 cutoffs); what the first run delivers.
+    #: ``None`` asks for every profile array over every plane (the reference's behaviour, 3x the bytes).
+    consumer_windows = None
+
     @classmethod
     def _run_mask(cls) -> int:
         return _RUN_MASK | (_lib.OUT_F32 if np.dtype(cls.profile_dtype) == np.float32 else 0)
+
+    def _request_spec(self):
+        """Per-sweep request (see ``_lib.make_requests``) of the first run."""
+        if self.consumer_windows is None:
+            return _lib.OUT_ALL_PROFILES
+        n = len(self._z_incrs)
+        spec = {}
+        for name, cutoff in self.consumer_windows.items():
+            lo, hi = int((1 - cutoff[1]) * n), int((1 - cutoff[0]) * n)
+            spec[_OUT_BIT[name]] = (lo, hi)
+        return spec
 
     def __init__(self, obb, zslice_num: int, interp_num: int, return_odd: bool = False):
         self._mesh_oriented_uobb = obb.mesh
@@ -66,8 +90,28 @@ class GpuSlices:
     def _result(self):
         if self._attached is not None:
             return self._attached
-        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], self._run_mask(), lazy=True)
+        res = _lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], self._run_mask(), lazy=True,
+                               requests=[self._request_spec()])
         return res, 0
+
+    def _result_for(self, name: str):
+        """A run that holds EVERY row of profile array ``name`` (made on first need, one per array)."""
+        cache = self.__dict__.setdefault("_full_runs", {})
+        if name not in cache:
+            cache[name] = (_lib.sweep_batch([self._mesh_arrays()], [self._sweep_spec(0)], self._run_mask(), lazy=True,
+                                            requests=[{_OUT_BIT[name]: (0, -1)}]), 0)
+        return cache[name]
+
+    def _profile_rows(self, name: str, lo: int, hi: int) -> np.ndarray:
+        """Rows [lo, hi) of cached array ``name``: from the first run when its window holds them, else from a full run."""
+        self._require_sections()
+        which = _PROFILE_ARRAYS[name]
+        res, k = self._result
+        wlo, whi = res.window(which, k)
+        if whi > wlo and wlo <= lo and hi <= whi:
+            return res.array(which, k)[lo - wlo:hi - wlo]
+        res, k = self._result_for(name)
+        return res.array(which, k)[lo:hi]
 
     @cached_property
     def _result_full(self):
@@ -139,26 +183,34 @@ class GpuSlices:
     def areas1(self, cutoff: tuple):
         return self._cutoff(self._areas1, cutoff)
 
+    def _cut_rows(self, name: str, cutoff: tuple) -> np.ndarray:
+        """``_cutoff(self.<name>, cutoff)`` without materialising rows nobody asked for."""
+        n = len(self._z_incrs)
+        idx = self._cutoff(range(n), cutoff)
+        if len(idx) == 0:
+            return self._profile_rows(name, 0, 0)
+        return self._profile_rows(name, idx[0], idx[-1] + 1)
+
     def ixy(self, cutoff: tuple):
-        return self._cutoff(self._ixy, cutoff)
+        return self._cut_rows("_ixy", cutoff)
 
     def ixy_centered(self, cutoff: tuple):
-        return self._cutoff(self._ixy_centered, cutoff)
+        return self._cut_rows("_ixy_centered", cutoff)
 
     def itr(self, cutoff: tuple) -> np.ndarray:
-        return self._cutoff(self._ixy, cutoff)            # sic: slice.py:99-100
+        return self._cut_rows("_ixy", cutoff)             # sic: slice.py:99-100
 
     def itr_start(self, cutoff: tuple):
-        return self._cutoff(self._itr_start, cutoff)
+        return self._cut_rows("_itr_start", cutoff)
 
     def itr_start_even_theta(self, cutoff: tuple):
-        return self._cutoff(self._itr_start, cutoff)      # sic: slice.py:121-122
+        return self._cut_rows("_itr_start", cutoff)       # sic: slice.py:121-122
 
     def itr_centered(self, cutoff: tuple):
-        return self._cutoff(self._itr_centered, cutoff)
+        return self._cut_rows("_itr_centered", cutoff)
 
     def itr_centered_start(self, cutoff: tuple):
-        return self._cutoff(self._itr_centered_start, cutoff)
+        return self._cut_rows("_itr_centered_start", cutoff)
 
     def zs(self, cutoff) -> np.ndarray:
         return self._cutoff(self._zs, cutoff)
@@ -171,8 +223,7 @@ class GpuSlices:
 
 def _profile_property(name: str, which: int):
     def get(self):
-        self._require_sections()
-        return self._arr(which)              # view of the result's pinned buffer (no host copy)
+        return self._profile_rows(name, 0, len(self._z_incrs))      # view of a result's pinned buffer (no host copy)
     get.__name__ = name
     prop = cached_property(get)
     prop.__set_name__(GpuSlices, name)
@@ -184,6 +235,8 @@ for _name, _which in _PROFILE_ARRAYS.items():
 
 
 class GpuFullSlices(GpuSlices):
+    consumer_windows = {}                                   # canal.py:40-46, surgical_neck.py:31-34: plane records only
+
     def __init__(self, obb, zslice_num=200, interp_num=100, return_odd=False):
         super().__init__(obb, zslice_num, interp_num, return_odd)
 
@@ -194,6 +247,9 @@ class GpuFullSlices(GpuSlices):
 
 
 class GpuProximalSlices(GpuSlices):
+    consumer_windows = {"_itr_start": (0.0, 0.852),         # anatomic_neck.py:34-36
+                        "_itr_centered_start": (0.2, 0.75)}  # bicipital_groove.py:161-162
+
     def __init__(self, obb, surgical_neck, zslice_num=600, interp_num=512, return_odd=False):
         # 600 x 512 "must not change": the anatomic-neck CNN input (slice.py:236-237)
         self.surgical_neck = surgical_neck
@@ -206,6 +262,8 @@ class GpuProximalSlices(GpuSlices):
 
 
 class GpuDistalSlices(GpuSlices):
+    consumer_windows = {}                                   # epicondyle.py:33-43: 37 polygons_closed[0] (contours, on demand)
+
     def __init__(self, obb, zslice_num=200, interp_num=500, return_odd=False):
         super().__init__(obb, zslice_num, interp_num, return_odd)
 
@@ -225,7 +283,8 @@ def run_batch(slices_objects, extra_mask: int = 0):
             mesh_id[key] = len(meshes)
             meshes.append(s._mesh_arrays())
         sweeps.append(s._sweep_spec(mesh_id[key]))
-    res = _lib.sweep_batch(meshes, sweeps, type(slices_objects[0])._run_mask() | extra_mask, lazy=True)
+    res = _lib.sweep_batch(meshes, sweeps, type(slices_objects[0])._run_mask() | extra_mask, lazy=True,
+                           requests=[s._request_spec() for s in slices_objects])
     for k, s in enumerate(slices_objects):
         s._attached = (res, k)
         s.__dict__.pop("_result", None)

@@ -62,7 +62,10 @@ def compare_sweep(vertices, faces, zs, interp_num, res=None, sweep=0, n_angles=0
     if len(runs) == 2:
         for name in _MODE_INDEPENDENT + (("ARR_RADIAL",) if n_angles else ()):
             a, b = runs["full"].array(getattr(_lib, name)), runs["fast"].array(getattr(_lib, name))
-            assert np.array_equal(a, b, equal_nan=True), f"{name}: FULL and FAST runs differ"
+            if name in ("ARR_AREA1", "ARR_CONTOUR_AREA"):       # fixed-order sums in both, but the two stitchers add in different orders
+                assert np.allclose(a, b, rtol=1e-13, atol=0), f"{name}: FULL and FAST runs differ"
+            else:
+                assert np.array_equal(a, b, equal_nan=True), f"{name}: FULL and FAST runs differ"
     for r in runs.values():
         r.close()
     return rep
