@@ -2,16 +2,20 @@
 """Benchmark of the multiplane slicing hot path (BASELINE.json metric: cross-section planes/sec;
 bones/sec and % of HBM roofline ride along in the same JSON line).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg3l3|cfg4]
 
 A "step" is one pass of the whole hot path (bucket -> intersect -> stitch -> resample/unroll)
-over one batch of synthetic bones.  Default workload = BASELINE.json configs[1]: the reference's
+over one batch of synthetic bones.  Headline workload = BASELINE.json configs[1]: the reference's
 ``humerus_left`` test bone under the config-4 jitter, 2,048 planes along the shaft axis per bone,
 outlines resampled to 360 points + the 360-ray radius image, ``--bones`` bones per step per GPU.
+The same line carries sub-records for the other BASELINE configs (``configs``: cfg3_L2 = 519,040 triangles,
+cfg3_L3 = 2,076,160 triangles, 8,192 planes each, sharded by plane range when N > 1; cfg4 = jittered test bones x the
+three default sweeps with the consumers' row windows, sharded by bone) and a ``parity`` block: one bone of the timed
+batch against the oracle, outside the timed region.
 
   value  planes/s with the batch already resident in HBM (shb_batch_run only), CUDA events
-  e2e    planes/s through the public host call (shb_sweep_batch): pinned host inputs -> H2D ->
-         kernels -> D2H of the arrays the Slices API serves, wall clock
+  e2e    planes/s through the public host call: pinned host inputs -> H2D -> kernels -> D2H of the
+         requested arrays, wall clock
   roofline      dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline  the numpy restatement of the trimesh path (oracle/) on a bounded sample, 1 core
 
@@ -35,6 +39,13 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 HBM_FALLBACK_GBS = 6650.0       # /opt/skills/guides/B200_PROFILING.md fallback
+NAMES = ["humerus_left", "humerus_right", "humerus_left_trab", "humerus_left_flipped"]
+WORKLOAD_DESC = {
+    "cfg2": "BASELINE configs[1]: humerus_left (config-4 jitter per bone), dense multiplane sweep along the shaft axis + radial unroll",
+    "cfg3": "BASELINE configs[2]: Loop-subdivided humerus_left, 519,040 triangles, single mesh",
+    "cfg3l3": "BASELINE configs[2]: Loop-subdivided humerus_left, 2,076,160 triangles, single mesh",
+    "cfg4": "BASELINE configs[3]: jittered test bones, the three default sweeps of bone.Humerus (200x100, 200x500, 600x512), consumers' row windows",
+}
 
 
 # ------------------------------------------------------------------------------------------
@@ -44,17 +55,16 @@ def make_bones(workload: str, n_bones: int, first_id: int, planes: int, interp: 
     """Returns (meshes, sweeps) in the packing order of shoulder_b200._lib._pack."""
     from shoulder_b200 import meshio
     base = meshio.load_mesh(ROOT / "tests" / "golden" / "bones" / "humerus_left.npz")
-    names = ["humerus_left", "humerus_right", "humerus_left_trab", "humerus_left_flipped"]
-    bases = {n: meshio.load_mesh(ROOT / "tests" / "golden" / "bones" / f"{n}.npz") for n in names} if workload == "cfg4" else None
+    bases = {n: meshio.load_mesh(ROOT / "tests" / "golden" / "bones" / f"{n}.npz") for n in NAMES} if workload == "cfg4" else None
     meshes, sweeps = [], []
     for i in range(n_bones):
         bid = first_id + i
-        if workload == "cfg3":
+        if workload in ("cfg3", "cfg3l3"):
             obb = meshio.PcaObb(base)
-            v, f = meshio.loop_subdivide(obb.mesh.vertices, obb.mesh.faces, 2)        # 519,040 triangles
+            v, f = meshio.loop_subdivide(obb.mesh.vertices, obb.mesh.faces, 2 if workload == "cfg3" else 3)
             m = meshio.Mesh(v, f)
         else:
-            src = bases[names[bid % 4]] if workload == "cfg4" else base
+            src = bases[NAMES[bid % 4]] if workload == "cfg4" else base
             m = meshio.PcaObb(meshio.synthetic_bone(src, bid)).mesh
         z = m.vertices[:, 2]
         k = len(meshes)
@@ -71,27 +81,44 @@ def make_bones(workload: str, n_bones: int, first_id: int, planes: int, interp: 
     return meshes, sweeps
 
 
+def consumer_requests(sweeps):
+    """cfg4: what the reference's consumers read of each default sweep (shoulder_b200/slice.py ``consumer_windows``):
+    Full (200x100) and Distal (200x500): plane records only (canal.py:40-46, surgical_neck.py:31-34,
+    epicondyle.py:33-43); Proximal (600x512): itr_start rows of cutoff (0, 0.852) (anatomic_neck.py:34-36) and
+    itr_centered_start rows of cutoff (0.2, 0.75) (bicipital_groove.py:161-162)."""
+    from shoulder_b200 import _lib
+    req = []
+    for (_, _, h, n) in sweeps:
+        P = len(h)
+        if P == 600 and n == 512:
+            req.append({_lib.OUT_ITR_START: (int((1 - 0.852) * P), int((1 - 0.0) * P)),
+                        _lib.OUT_ITR_CENTERED_START: (int((1 - 0.75) * P), int((1 - 0.2) * P))})
+        else:
+            req.append({})
+    return req
+
+
 # ------------------------------------------------------------------------------------------
 # CPU restatement (oracle) timing — the reference arm and the cpu_baseline leg
 # ------------------------------------------------------------------------------------------
 def _cpu_one(args):
+    """What the reference computes per sweep on the CPU: section_multiplane + the cached arrays its consumers read.
+    The oracle-only extras are off (comparison of the two merge rules, the O(m^2) numpy stand-in for GEOS is_valid —
+    skipping the latter favours the CPU arm) and the radius image (not a reference product) is not computed."""
     import oracle
-    from oracle.slice_arrays import radial_image
-    v, f, zs, n, angles = args
-    s = oracle.OracleSlices(v, f, zs, n, merge="hash", version="4")
+    v, f, zs, n = args
+    s = oracle.OracleSlices(v, f, zs, n, merge="hash", version="4", check_merge=False, validate=False)
     _ = (s.centroids, s.areas1, s.ixy, s.itr_start, s.itr_centered_start)
-    if angles:
-        radial_image(s.paths, angles)
     return len(zs)
 
 
-def cpu_jobs(meshes, sweeps, angles, max_planes=None):
+def cpu_jobs(meshes, sweeps, max_planes=None):
     jobs = []
     for (k, zo, h, n) in sweeps:
         zs = np.asarray(h) + zo
         if max_planes is not None and len(zs) > max_planes:
             zs = zs[:: len(zs) // max_planes][:max_planes]
-        jobs.append((meshes[k][0], meshes[k][1], zs, n, angles))
+        jobs.append((meshes[k][0], meshes[k][1], zs, n))
     return jobs
 
 
@@ -154,19 +181,33 @@ def hbm_peak():
 def stage_alg_bytes(stage: str, c: dict) -> float:
     """Compulsory HBM bytes of one launch of each stage: every input it must
     read once and every output it must write once; hash tables, sort passes and re-gathers of the
-    L2-resident mesh are NOT credited."""
-    V, T, S, P, C, PN, items, A = c["V"], c["T"], c["S"], c["P"], c["C"], c["PN"], c["items"], c["PA"]
+    L2-resident mesh are NOT credited.  ``PNk`` = delivered profile elements (rows x 2 x N summed over the requested
+    arrays), ``PA`` = delivered radius-image elements, ``Sres`` / ``Cres`` = segments / contours of the planes the
+    resample launch covers."""
+    V, T, S, P, C, items = c["V"], c["T"], c["S"], c["P"], c["C"], c["items"]
     if stage == "bucket":
         return 16 * T + 8 * V + 8 * P + 8 * items
     if stage == "scatter":
         return 8 * items + 16 * c["M"]
-    if stage == "intersect":    # bucketed triangles + mesh z in; 16-byte hit records out (one pass)
+    if stage == "intersect":    # bucketed triangles + mesh z + face adjacency in; 16-byte hit records out (one pass)
         return 16 * c["M"] + 16 * T + 8 * V + 8 * P + 16 * S
-    if stage == "stitch":       # hit records + mesh once in; closed contours + plane records out (+ face_index, segments when requested)
-        return 16 * S + 16 * T + 32 * V + (36 * S if c.get("full") else 0) + 16 * (S + C) + 20 * C + 200 * P
-    if stage == "resample":     # chosen outlines in; k profile arrays + radius image out
-        return 16 * (S + C) + 8 * c["k"] * 2 * PN + 8 * A + 88 * P
+    if stage == "stitch":       # hit records + the vertices the crossings need once in; closed contours + plane records out
+        return 16 * S + 32 * V + (36 * S + 16 * T if c.get("full") else 0) + 16 * (S + C) + 20 * C + 200 * P
+    if stage == "resample":     # chosen outlines in; requested profile rows + radius image out
+        return 16 * (c["Sres"] + c["Cres"]) + c["esz"] * c["PNk"] + c["esz"] * c["PA"] + 88 * c["Pres"]
     return 8 * P * 6
+
+
+def workload_config(workload, bones, planes, interp, angles, world):
+    cfg = {"workload": WORKLOAD_DESC[workload], "bones_per_step_per_gpu": bones,
+           "planes_per_bone": planes if workload != "cfg4" else 1000,
+           "interp_num": interp if workload != "cfg4" else "100/500/512", "radial_angles": angles,
+           "triangles_per_bone": {"cfg3": 519040, "cfg3l3": 2076160}.get(workload, 32440),
+           "l2": "256 MiB buffer written between timed steps (L2 flush)",
+           "sharding": "by contiguous plane range of the one mesh, no collective" if workload.startswith("cfg3") else "by bone, no data-path collective"}
+    if workload.startswith("cfg3") and world > 1:
+        cfg["planes_per_gpu"] = planes // world
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------
@@ -177,9 +218,10 @@ def run_reference(args, rank, world):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    n_bones = min(args.bones, cores) if args.workload != "cfg3" else 1
+    single = args.workload.startswith("cfg3")
+    n_bones = min(args.bones, cores) if not single else 1
     meshes, sweeps = make_bones(args.workload, n_bones, 0, args.planes, args.interp)
-    jobs = cpu_jobs(meshes, sweeps, args.angles, max_planes=args.ref_planes)
+    jobs = cpu_jobs(meshes, sweeps, max_planes=args.ref_planes)
     planes_per_step = sum(len(j[2]) for j in jobs)
     with mp.get_context("fork").Pool(min(cores, len(jobs))) as pool:
         for _ in range(args.warmup_ref):
@@ -190,242 +232,363 @@ def run_reference(args, rank, world):
         dt = time.perf_counter() - t0
     value = planes_per_step * args.steps_ref / dt
     used = min(cores, len(jobs))
+    per_sweep = sorted({len(j[2]) for j in jobs})
     sample = (f"{n_bones} bone(s) x {len(jobs) // max(n_bones, 1)} sweep(s), {planes_per_step} planes per step "
-              f"(at most {args.ref_planes} planes per sweep), "
-              f"numpy restatement of the trimesh path, multiprocessing over sweeps")
+              f"({'/'.join(map(str, per_sweep))} planes per sweep: an even subsample of the workload's planes), numpy restatement of "
+              f"the trimesh path (section_multiplane + centroids, areas1, ixy, itr_start, itr_centered_start; no radius image), "
+              f"multiprocessing over sweeps on {used} of {cores} cores")
+    cfg = workload_config(args.workload, args.bones if not single else 1, args.planes, args.interp, args.angles, 1)      # the workload both arms are quoted on
+    ran = {"bones_per_step": n_bones, "planes_per_sweep": per_sweep, "planes_per_step": planes_per_step,
+           "note": "a bounded sample of the config's workload ran: throughput is per plane, so sample and full workload are "
+                   "comparable; the radius image (not a reference product) is not computed on the CPU"}
     line = {
         "impl": "reference", "metric": "planes_per_sec", "value": value, "unit": "planes/s", "n_gpus": args.gpus,
         "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": 1e3 * dt / args.steps_ref, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, args.bones if args.workload != "cfg3" else 1),
-        "bones_per_sec": n_bones * args.steps_ref / dt,
+        "config": cfg, "ran": ran,
+        "bones_per_sec": value / cfg["planes_per_bone"],
         "cpu_baseline": {"value": value, "unit": "planes/s", "cores": used, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "planes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "trimesh is not installable in this image; this is the oracle/ restatement of its algorithm (parity unpinned)",
+        "note": "trimesh is not installable in this image; this is the oracle/ restatement of its algorithm (post-trimesh half pinned to the reference's slice.py, trimesh half unpinned)",
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args, bones):
-    desc = {"cfg2": "BASELINE configs[1]: humerus_left (config-4 jitter per bone), dense multiplane sweep along the shaft axis + radial unroll",
-            "cfg3": "BASELINE configs[2]: Loop-subdivided humerus_left, 519,040 triangles, single mesh",
-            "cfg4": "BASELINE configs[3]: jittered test bones, the three default sweeps of bone.Humerus (200x100, 200x500, 600x512)"}
-    return {"workload": desc[args.workload], "bones_per_step_per_gpu": bones, "planes_per_bone": args.planes if args.workload != "cfg4" else 1000,
-            "interp_num": args.interp if args.workload != "cfg4" else "100/500/512", "radial_angles": args.angles,
-            "triangles_per_bone": 32440 if args.workload != "cfg3" else 519040,
-            "l2": "256 MiB buffer written between timed steps (L2 flush)",
-            "sharding": "by contiguous plane range of the one mesh, no collective" if args.workload == "cfg3" else "by bone, no data-path collective"}
 
 
 # ------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
-    import torch
-    from shoulder_b200 import _lib
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: shoulder_b200 has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        # stdout carries the ONE JSON line and nothing else: NCCL prints its version banner there when the first
-        # communicator comes up, so fd 1 points at stderr until that has happened
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    _lib.init(local_rank)
-    # an explicit (non-NULL) stream: the library enqueues on it and the torch events below are recorded on it
-    stream = torch.cuda.Stream()
-    torch.cuda.set_stream(stream)
-    assert stream.cuda_stream != 0
-    _lib.set_stream(stream.cuda_stream)
+class Gpu:
+    """Per-process device state shared by the workloads of one bench run."""
 
-    bones = args.bones if args.workload != "cfg3" else 1
-    meshes, sweeps = make_bones(args.workload, bones, rank * bones if args.workload != "cfg3" else 0, args.planes, args.interp)
-    if args.workload == "cfg3" and world > 1:
+    def __init__(self, rank, world, local_rank):
+        import torch
+        from shoulder_b200 import _lib
+        self.torch, self.lib, self.rank, self.world, self.local_rank = torch, _lib, rank, world, local_rank
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: shoulder_b200 has no CPU path")
+        torch.cuda.set_device(local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            # stdout carries the ONE JSON line and nothing else: NCCL prints its version banner there when the first
+            # communicator comes up, so fd 1 points at stderr until that has happened
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+            self.dist = dist
+        _lib.init(local_rank)
+        # an explicit (non-NULL) stream: the library enqueues on it and the torch events below are recorded on it
+        self.stream = torch.cuda.Stream()
+        torch.cuda.set_stream(self.stream)
+        assert self.stream.cuda_stream != 0
+        _lib.set_stream(self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, vals, op="max"):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+
+def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2e_chunks, sampler=None, f32_leg=True):
+    """Device-resident leg + end-to-end leg of one workload on this rank; returns the record (rank-reduced)."""
+    torch, _lib = gpu.torch, gpu.lib
+    rank, world = gpu.rank, gpu.world
+    single = workload.startswith("cfg3")
+    nb = 1 if single else bones
+    meshes, sweeps = make_bones(workload, nb, 0 if single else rank * nb, planes, interp)
+    if single and world > 1:
         # one large mesh: replicate it, shard the sweep by contiguous plane range (z_orig stays the full-list mean)
         from shoulder_b200 import sharding
         k, zo, h, n = sweeps[0]
         lo, hi = sharding.shard_planes(len(h), rank, world)
         sweeps = [(k, zo, h[lo:hi], n)]
     packed = list(_lib._pack(meshes, sweeps))
-    # pinned host copies: the e2e leg copies from pinned memory
-    pinned = []
-    for a in packed:
-        t = torch.from_numpy(a).pin_memory()
-        pinned.append(t)
+    pinned = [torch.from_numpy(a).pin_memory() for a in packed]         # the e2e leg copies from pinned memory
     packed_pinned = tuple(t.numpy() for t in pinned)
     h2d = int(sum(a.nbytes for a in packed_pinned))
     planes_per_step = int(packed[7][-1])
-    mask_dev = _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_ITR_START | _lib.OUT_ITR_CENTERED_START | (_lib.OUT_RADIAL if args.angles else 0)
-    k_prof = 3
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+    if workload == "cfg4":
+        mask, requests, angles = _lib.OUT_PLANE, consumer_requests(sweeps), 0
+    else:
+        mask = _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_ITR_START | _lib.OUT_ITR_CENTERED_START | (_lib.OUT_RADIAL if angles else 0)
+        requests = None
+    flush, stream = gpu.flush, gpu.stream
 
     # ---------------- device-resident leg -------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     batch = _lib.SweepBatch(None, None, packed=packed_pinned)
     counts = None
-    for _ in range(args.warmup):
-        r = batch.run(mask_dev, args.angles)
+    for _ in range(warmup):
+        r = batch.run(mask, angles, requests)
         if counts is None:
-            tot = r.totals()
-            counts = tot
+            counts = r.totals()
         r.close()
     torch.cuda.synchronize()
     # every stage timed once, OUTSIDE the timed region, for the stage table; inside the timed region only the three
     # heavy stages carry event pairs (an event pair costs ~3 us of device time, all seven ~2.5 % of this step)
     _lib.profile_enable(True)
     _lib.profile_read(reset=True)
-    n_tab = max(2, min(args.steps, 5))
+    n_tab = max(2, min(steps, 5))
     for _ in range(n_tab):
         flush.fill_(1)
-        batch.run(mask_dev, args.angles).close()
+        batch.run(mask, angles, requests).close()
     torch.cuda.synchronize()
     stage_table = {n: v[0] / n_tab for n, v in _lib.profile_read(reset=True).items()}
     heavy = ("intersect", "stitch", "resample")
     _lib.profile_enable(True, stages=heavy)
-    barrier()
+    gpu.barrier()
     t_dev0 = time.perf_counter()
     launches0 = _lib.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     for a, b in ev:
         flush.fill_(1)                      # L2 flush, outside the timed events
         a.record(stream)
-        r = batch.run(mask_dev, args.angles)
+        r = batch.run(mask, angles, requests)
         b.record(stream)
         r.close()
-    barrier()
-    sampler.window(t_dev0, time.perf_counter())
+    gpu.barrier()
+    if sampler:
+        sampler.window(t_dev0, time.perf_counter())
     launches = _lib.launch_count() - launches0
     ms = sum(a.elapsed_time(b) for a, b in ev)
     stages = {n: v for n, v in _lib.profile_read(reset=True).items() if n in heavy}      # measured live, inside the timed region
     _lib.profile_enable(False)
+    batch.close()
 
     # ---------------- end-to-end leg (public host call) -----------------------------------
     # the batch is handed over as `e2e_chunks` groups of whole bones (pinned host arrays); the library overlaps
     # each group's device->host copy with the next group's upload + kernels.  Every step moves every input byte
-    # host->device and every output byte device->host.
-    mask_e2e = mask_dev
-    chunks, first = _lib.split_packed(packed_pinned, args.e2e_chunks)
+    # host->device and every requested output byte device->host.
+    chunks, first = _lib.split_packed(packed_pinned, e2e_chunks)
     chunks = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in c) for c in chunks]
+    fetched = [_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_STATUS, _lib.ARR_SEL, _lib.ARR_BOUNDS, _lib.ARR_CENTROID, _lib.ARR_AREA1]
+    windowed = [(_lib.ARR_IXY, _lib.OUT_IXY), (_lib.ARR_ITR_START, _lib.OUT_ITR_START),
+                (_lib.ARR_ITR_CENTERED_START, _lib.OUT_ITR_CENTERED_START), (_lib.ARR_RADIAL, _lib.OUT_RADIAL)]
+    fetch_mask = mask | _lib.OUT_ITR_START | _lib.OUT_ITR_CENTERED_START if requests is not None else mask
 
-    def e2e_call(mask):
-        return _lib.sweep_batch_pipelined(chunks, first, mask, args.angles)
+    def e2e_call(extra=0):
+        return _lib.sweep_batch_pipelined(chunks, first, fetch_mask | extra, angles, requests)
 
-    for _ in range(max(2, args.warmup)):
-        r = e2e_call(mask_e2e)
-        r.close()
-    barrier()
-    d2h = 0
+    def count_d2h(r):
+        d2h, prof_elems, rad_elems, pres = 0, 0, 0, set()
+        for s in range(r.n_sweep):
+            for w in fetched:
+                d2h += r.array(w, s).nbytes
+            d2h += 4 * len(r.array(_lib.ARR_SEG_OFF, s))
+            for w, bit in windowed:
+                want = (requests[s].get(bit) is not None) if requests is not None else bool(mask & bit)
+                if want:
+                    a = r.array(w, s)
+                    d2h += a.nbytes
+                    if w == _lib.ARR_RADIAL:
+                        rad_elems += a.size
+                    else:
+                        prof_elems += a.size
+        return d2h, prof_elems, rad_elems
+
+    for _ in range(max(2, warmup)):
+        e2e_call().close()
+    gpu.barrier()
+    d2h = prof_elems = rad_elems = 0
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        r = e2e_call(mask_e2e)
+    for i in range(steps):
+        r = e2e_call()
         if i == 0:
-            for s in range(r.n_sweep):
-                for w in (_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_STATUS, _lib.ARR_SEL, _lib.ARR_BOUNDS, _lib.ARR_CENTROID,
-                          _lib.ARR_AREA1, _lib.ARR_IXY, _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START):
-                    d2h += r.array(w, s).nbytes
-                d2h += 4 * (len(r.array(_lib.ARR_SEG_OFF, s)))
-                if args.angles:
-                    d2h += r.array(_lib.ARR_RADIAL, s).nbytes
+            d2h, prof_elems, rad_elems = count_d2h(r)
         r.close()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    sampler.window(t0, t0 + e2e_s)
-    # same call with float32 profile / radius outputs (SHB_OUT_F32), reported beside the float64 headline
-    for _ in range(2):
-        e2e_call(mask_e2e | _lib.OUT_F32).close()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    for i in range(args.steps):
-        e2e_call(mask_e2e | _lib.OUT_F32).close()
-    torch.cuda.synchronize()
-    e2e32_s = time.perf_counter() - t1
-    clocks = sampler.stop()
+    if sampler:
+        sampler.window(t0, t0 + e2e_s)
+    e2e32_s = None
+    if f32_leg:      # same call with float32 profile / radius outputs (SHB_OUT_F32), reported beside the float64 headline
+        for _ in range(2):
+            e2e_call(_lib.OUT_F32).close()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for i in range(steps):
+            e2e_call(_lib.OUT_F32).close()
+        torch.cuda.synchronize()
+        e2e32_s = time.perf_counter() - t1
 
     # ---------------- reduce over ranks ----------------------------------------------------
-    tvals = torch.tensor([ms, e2e_s * 1e3, e2e32_s * 1e3], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(tvals, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, e2e32_ms_max = float(tvals[0]), float(tvals[1]), float(tvals[2])
-    ptot = torch.tensor([planes_per_step], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(ptot, op=dist.ReduceOp.SUM)
-    total_planes = int(ptot.item())
-    value = total_planes * args.steps / (ms_max * 1e-3)
-    e2e_value = total_planes * args.steps / (e2e_ms_max * 1e-3)
+    ms_max, e2e_ms_max, e2e32_ms_max = gpu.reduce([ms, e2e_s * 1e3, (e2e32_s or 0.0) * 1e3])
+    total_planes = int(gpu.reduce([planes_per_step], "sum")[0])
+    total_bones = nb * world if not single else 1
+    value = total_planes * steps / (ms_max * 1e-3)
+    e2e_value = total_planes * steps / (e2e_ms_max * 1e-3)
 
-    # ---------------- roofline of the dominant kernel (rank 0, its own GPU) ---------------
+    # ---------------- roofline of the dominant kernel (this rank's GPU) --------------------
     V = int(packed[1][-1]); T = int(packed[3][-1])
     S = counts["segments"]; Cn = counts["contours"]; P = planes_per_step
-    PN = int(sum(len(s[2]) * s[3] for s in sweeps)); PA = P * args.angles
     items = int(sum(len(meshes[s[0]][1]) for s in sweeps))
-    c = {"V": V, "T": T, "S": S, "P": P, "C": Cn, "PN": PN, "items": items, "M": items, "PA": PA, "k": k_prof}
+    if requests is None:
+        Pres, frac_res = P, 1.0
+    else:
+        Pres = sum(max((hi - lo for (lo, hi) in q.values()), default=0) for q in requests)
+        frac_res = Pres / max(P, 1)
+    c = {"V": V, "T": T, "S": S, "P": P, "C": Cn, "items": items, "M": items, "PNk": prof_elems, "PA": rad_elems, "esz": 8,
+         "Pres": Pres, "Sres": S * frac_res, "Cres": Cn * frac_res}
     dom = max(stages, key=lambda n: stages[n][0])
-    dom_ms = stages[dom][0] / args.steps
+    dom_ms = stages[dom][0] / steps
     peak, peak_kind = hbm_peak()
     alg = stage_alg_bytes(dom, c)
     achieved = alg / (dom_ms * 1e-3) / 1e9
     # whole step: inputs once + the outputs this run delivers (intermediates such as hit lists and contour points are not credited)
-    pipeline_alg = 24 * V + 12 * T + 8 * k_prof * 2 * PN + 8 * PA + 76 * P
-    traffic = None
-    tfile = ROOT / "profiles" / "r1g_traffic.json"
-    if tfile.exists() and args.workload == "cfg2" and bones == 32 and args.planes == 2048 and args.interp == 360 and args.angles == 360:
-        for name, rec in json.loads(tfile.read_text())["kernels"].items():     # ncu --set full capture of this very command
-            if name.startswith("k_" + dom) and not name.endswith("<0>"):
-                traffic = rec["traffic_bytes"]
+    pipeline_alg = 24 * V + 12 * T + 8 * prof_elems + 8 * rad_elems + 76 * P
+    step_ms = ms_max / steps
     roofline = {"bound": "hbm", "kernel": "k_" + dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "alg_bytes_per_launch": alg, "ms_per_launch": dom_ms,
-                "stage_ms_per_step": {n: (stages[n][0] / args.steps if n in stages else stage_table[n]) for n in stage_table},
-                "pipeline": {"alg_bytes_per_step": pipeline_alg, "achieved": pipeline_alg / (ms_max / args.steps * 1e-3) / 1e9,
-                             "frac": pipeline_alg / (ms_max / args.steps * 1e-3) / 1e9 / peak}}
+                "frac": achieved / peak, "traffic": None, "alg_bytes_per_launch": alg, "ms_per_launch": dom_ms,
+                "stage_ms_per_step": {n: (stages[n][0] / steps if n in stages else stage_table[n]) for n in stage_table},
+                "stage_frac": {n: stage_alg_bytes(n, c) / ((stages[n][0] / steps) * 1e-3) / 1e9 / peak for n in stages if stages[n][0] > 0},
+                "pipeline": {"alg_bytes_per_step": pipeline_alg, "achieved": pipeline_alg / (step_ms * 1e-3) / 1e9,
+                             "frac": pipeline_alg / (step_ms * 1e-3) / 1e9 / peak}}
+    rec = {
+        "value": value, "unit": "planes/s", "ms_per_step": step_ms, "scaling": "strong" if single else "weak",
+        "config": workload_config(workload, nb, planes, interp, angles, world),
+        "bones_per_sec": total_bones * steps / (ms_max * 1e-3),
+        "segments_per_step_per_gpu": S, "contours_per_step_per_gpu": Cn,
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": "planes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_max / steps, "bones_per_sec": total_bones * steps / (e2e_ms_max * 1e-3),
+                "d2h_bytes_per_bone": d2h / max(nb, 1),
+                "outputs": ("plane records + the consumers' windows: itr_start rows 88..599 and itr_centered_start rows 150..479 of the proximal sweep, float64"
+                            if requests is not None else "plane records + ixy + itr_start + itr_centered_start (+ radius image), float64, every plane"),
+                "call": f"shoulder_b200._lib.sweep_batch_pipelined, {len(chunks)} group(s) of bones"},
+        "gpu_launches": int(launches),
+    }
+    if e2e32_s is not None:
+        rec["e2e_f32"] = {"value": total_planes * steps / (e2e32_ms_max * 1e-3), "unit": "planes/s",
+                          "ms_per_step": e2e32_ms_max / steps, "note": "same call with SHB_OUT_F32 (float32 profile arrays)"}
+    return rec, (meshes, sweeps, mask, angles, requests)
 
+
+def parity_block(gpu: Gpu, meshes, sweeps, mask, angles, max_planes=2048):
+    """One bone of the timed batch against the oracle, outside the timed region, through the kernel instantiations
+    the bench times (no SHB_OUT_SEGMENTS)."""
+    import oracle
+    from oracle.slice_arrays import radial_image, rows_for_paths
+    _lib = gpu.lib
+    k, zo, h, n = sweeps[0]
+    v, f = meshes[k]
+    h = np.asarray(h)
+    idx = np.arange(len(h)) if len(h) <= max_planes else np.linspace(0, len(h) - 1, max_planes).astype(int)
+    t0 = time.perf_counter()
+    res = _lib.sweep_batch([(v, f)], [(0, zo, h, n)], mask | _lib.OUT_CONTOURS, angles)
+    paths = oracle.section_multiplane(v, f, [0, 0, zo], [0, 0, 1], h[idx], merge="topo")
+    good = [j for j, p in enumerate(paths) if p is not None and p.info["agree"] and all(p.entity_closed(e) for e in range(len(p.entities)))]
+    ii, pp = idx[good], [paths[j] for j in good]
+    rows = rows_for_paths(pp, n)
+    rel = lambda a, b: float(np.abs(np.asarray(a) - b).max() / max(np.abs(b).max(), 1e-300))
+    ct_off, ctpt, pts = res.array(_lib.ARR_CONTOUR_OFF), res.array(_lib.ARR_CONTOUR_PT_OFF), res.array(_lib.ARR_POINTS)
+    contours_equal = 0
+    for i, p in zip(ii, pp):
+        c0 = int(ct_off[i])
+        contours_equal += all(np.array_equal(pts[int(ctpt[c0 + c]):int(ctpt[c0 + c + 1])], dsc) for c, dsc in enumerate(p.discrete))
+    out = {
+        "checked": f"bone 0 of the timed batch, {len(ii)} of {len(h)} planes, against oracle/ (numpy restatement; post-trimesh half pinned to the reference's slice.py)",
+        "planes": int(len(ii)),
+        "n_seg_equal": bool(np.array_equal(res.array(_lib.ARR_N_SEG)[ii], [len(p.metadata["face_index"]) for p in pp])),
+        "n_entities_equal": bool(np.array_equal(res.array(_lib.ARR_N_ENT)[ii], [len(p.entities) for p in pp])),
+        "contours_bit_equal": int(contours_equal),
+        "centroid_bit_equal": bool(np.array_equal(res.array(_lib.ARR_CENTROID)[ii], rows["centroids"])),
+        "area1_max_rel": rel(res.array(_lib.ARR_AREA1)[ii], rows["areas1"]),
+        "planes_with_merged_vertices": int(sum(1 for p in pp if p.info.get("n_merged"))),
+        "tolerance": "bit-exact contours / centroids; 1e-12 areas; 1e-9 profiles (north_star budget 1e-5)",
+    }
+    for name, which, bit in (("ixy", _lib.ARR_IXY, _lib.OUT_IXY), ("itr_start", _lib.ARR_ITR_START, _lib.OUT_ITR_START),
+                             ("itr_centered_start", _lib.ARR_ITR_CENTERED_START, _lib.OUT_ITR_CENTERED_START)):
+        if mask & bit:
+            out[name + "_max_rel"] = rel(res.array(which)[ii], rows[name])
+    if angles:
+        out["radial_max_rel"] = rel(res.array(_lib.ARR_RADIAL)[ii], radial_image(pp, angles))
+    errs = [v for kk, v in out.items() if kk.endswith("_max_rel")]
+    out["ok"] = bool(out["n_seg_equal"] and out["n_entities_equal"] and out["centroid_bit_equal"] and contours_equal == len(ii)
+                     and out["area1_max_rel"] < 1e-12 and all(e < 1e-9 for e in errs))
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    res.close()
+    return out
+
+
+def traffic_from_profiles(workload, dom):
+    """ncu --set full DRAM bytes of the dominant kernel, from the committed capture of this very command (labelled:
+    it is NOT measured in this run — a bench number is never taken under ncu)."""
+    tfile = ROOT / "profiles" / "r2_traffic.json"
+    if not tfile.exists() or workload != "cfg2":
+        return None, None
+    for name, rec in json.loads(tfile.read_text())["kernels"].items():
+        if name.startswith("k_" + dom):
+            return rec["traffic_bytes"], "profiles/r2_traffic.json: ncu --set full capture of `python bench.py --steps 2 --warmup 3 --no-cpu --no-sub` (committed; not measured in this run)"
+    return None, None
+
+
+def run_ours(args, rank, world, local_rank):
+    gpu = Gpu(rank, world, local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    rec, (meshes, sweeps, mask, angles, requests) = measure(gpu, args.workload, args.bones, args.planes, args.interp, args.angles,
+                                                            args.steps, args.warmup, args.e2e_chunks, sampler)
+    clocks = sampler.stop()
+    dom = rec["roofline"]["kernel"][2:]
+    rec["roofline"]["traffic"], rec["roofline"]["traffic_source"] = traffic_from_profiles(args.workload, dom)
+    # ---------------- the other BASELINE configs, same run, fewer steps --------------------
+    subs = {}
+    if not args.no_sub and args.workload == "cfg2":
+        sub_steps = max(3, min(args.steps, 5))
+        for name, wl, bones in (("cfg3_L2", "cfg3", 1), ("cfg3_L3", "cfg3l3", 1), ("cfg4", "cfg4", args.bones)):
+            try:
+                r, _ = measure(gpu, wl, bones, 8192, 360, 360, sub_steps, 3, args.e2e_chunks if wl == "cfg4" else 1, None, f32_leg=False)
+                r["steps"] = sub_steps
+                subs[name] = r
+            except Exception as e:          # a sub-record must not take the headline down
+                subs[name] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
+        if gpu.dist is not None:
+            gpu.dist.destroy_process_group()
         return
+    # ---------------- parity of the timed batch (rank 0) -----------------------------------
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(gpu, meshes, sweeps, mask, angles)
+        except Exception as e:
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"}
     # ---------------- CPU baseline on a bounded sample (rank 0, N=1 only) -----------------
     cpu = None
     if world == 1 and not args.no_cpu:
         n_pl, nb, t0 = 0, 0, time.perf_counter()
         while time.perf_counter() - t0 < 12.0 and nb < len(meshes):          # >= ~12 s of CPU work, whole bones
-            for j in cpu_jobs(meshes, [s for s in sweeps if s[0] == nb], args.angles, max_planes=args.cpu_planes):
+            for j in cpu_jobs(meshes, [s for s in sweeps if s[0] == nb], max_planes=args.cpu_planes):
                 n_pl += _cpu_one(j)
             nb += 1
         dt = time.perf_counter() - t0
         cpu = {"value": n_pl / dt, "unit": "planes/s", "cores": 1, "kind": "port",
-               "sample": f"first {nb} bone(s) of the batch, {n_pl} planes, {dt:.1f} s of single-thread numpy (oracle/ restatement of the trimesh path)"}
+               "sample": f"first {nb} bone(s) of the batch, {n_pl} planes, {dt:.1f} s of single-thread numpy (oracle/ restatement of the trimesh path, no radius image)"}
     line = {
-        "metric": "planes_per_sec", "value": value, "unit": "planes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong" if args.workload == "cfg3" else "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(args, bones),
-        "bones_per_sec": bones * world * args.steps / (ms_max * 1e-3),
-        "segments_per_step_per_gpu": S, "contours_per_step_per_gpu": Cn,
-        "roofline": roofline, "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "planes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms_max / args.steps, "bones_per_sec": bones * world * args.steps / (e2e_ms_max * 1e-3),
-                "outputs": "plane records + ixy + itr_start + itr_centered_start (+ radius image), float64, every plane",
-                "call": f"shoulder_b200._lib.sweep_batch_pipelined, {len(chunks)} groups of bones"},
-        "e2e_f32": {"value": total_planes * args.steps / (e2e32_ms_max * 1e-3), "unit": "planes/s",
-                    "ms_per_step": e2e32_ms_max / args.steps, "note": "same call with SHB_OUT_F32 (float32 profile arrays)"},
-        "gpu_launches": int(launches), "clocks": clocks,
+        "metric": "planes_per_sec", "value": rec["value"], "unit": "planes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": rec["scaling"], "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": rec["config"], "bones_per_sec": rec["bones_per_sec"],
+        "segments_per_step_per_gpu": rec["segments_per_step_per_gpu"], "contours_per_step_per_gpu": rec["contours_per_step_per_gpu"],
+        "roofline": rec["roofline"], "cpu_baseline": cpu, "e2e": rec["e2e"], "e2e_f32": rec.get("e2e_f32"),
+        "gpu_launches": rec["gpu_launches"], "clocks": clocks, "parity": parity, "configs": subs,
     }
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    if gpu.dist is not None:
+        gpu.dist.destroy_process_group()
 
 
 def main():
@@ -434,7 +597,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg3l3", "cfg4"])
     ap.add_argument("--bones", type=int, default=32, help="bones per step per GPU")
     ap.add_argument("--planes", type=int, default=None)
     ap.add_argument("--interp", type=int, default=360)
@@ -442,14 +605,19 @@ def main():
     ap.add_argument("--cpu-planes", type=int, default=None, help="planes per sweep in the cpu_baseline sample")
     ap.add_argument("--ref-planes", type=int, default=None, help="planes per sweep in one reference-arm step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the cfg3 / cfg4 sub-records")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="groups of bones the e2e call pipelines (D2H of one overlaps compute of the next)")
     args = ap.parse_args()
+    single = args.workload.startswith("cfg3")
     if args.planes is None:
-        args.planes = 8192 if args.workload == "cfg3" else 2048
-    if args.workload == "cfg3" and args.cpu_planes is None:
-        args.cpu_planes = 512
-    if args.workload == "cfg3" and args.ref_planes is None:
+        args.planes = 8192 if single else 2048
+    if single and args.cpu_planes is None:
+        args.cpu_planes = 512 if args.workload == "cfg3" else 128
+    if single and args.ref_planes is None:
         args.ref_planes = 16
+    if single:
+        args.e2e_chunks = 1
     args.warmup = max(args.warmup, 3)
     # the reference arm keeps the driver's K and W; its per-step sample is bounded so the run ends in minutes
     args.steps_ref, args.warmup_ref = args.steps, args.warmup

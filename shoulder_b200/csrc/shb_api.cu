@@ -49,6 +49,8 @@ struct Ctx {
     size_t smem_optin = 0;
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t copy = nullptr;           // device->host copies run here so they overlap the next batch's kernels
+    cudaStream_t aux = nullptr;            // the declined planes of the first part of a stitch launch run here, beside the bulk
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t sized = nullptr;           // recorded behind the size publication of a run
     int64_t launches = 0;
     uint32_t profile = 0;                  // bit s: stage s is timed
@@ -216,6 +218,9 @@ SHB_API int shb_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
     g.stream = g.own;
     CK(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.sized, cudaEventDisableTiming));
     // a private pool: its "never release on its own" threshold must not leak into other users of cudaMallocAsync
     cudaMemPoolProps props = {};
@@ -561,7 +566,7 @@ SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32
     CK(dalloc(&d.totals, 16, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
     CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
     CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
-    CK(dalloc(&d.o_sel, 2 * (size_t)G, st)); CK(dalloc(&d.decl_list, G, st)); CK(dalloc(&d.dup_list, G, st));
+    CK(dalloc(&d.o_sel, 2 * (size_t)G, st)); CK(dalloc(&d.decl_list, 2 * (size_t)G, st)); CK(dalloc(&d.dup_list, G, st));
     CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, ((size_t)G + 1) * sizeof(uint32_t), st));
     CK(cudaMemsetAsync(d.totals, 0, 16 * sizeof(uint32_t), st));
@@ -640,7 +645,7 @@ SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32
 
     { StageTimer t(3, st); t.stop(shb_launch_intersect(d, st)); }
     { StageTimer t(4, st); t.stop(shb_launch_scan_counts(d, st)); }
-    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, b->max_faces, budget, g.n_sm, st)); }
+    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, b->max_faces, budget, g.n_sm, st, g.aux, g.ev_fork, g.ev_join)); }
     if (any_prof) { StageTimer t(6, st); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)

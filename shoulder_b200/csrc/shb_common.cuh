@@ -83,7 +83,7 @@ struct ShbDev {
                           //       tag 3 = a vertex on the plane (the stitcher classifies such faces itself)
     uint32_t* seg_off;    // [G+1] exact segment offsets, original plane order
     uint32_t* big_list;   // [G]   planes too large for shared memory
-    uint32_t* decl_list;  // [G]   planes the warp stitcher declined (several contours, on-plane vertices, open / non-manifold
+    uint32_t* decl_list;  // [2 G] planes the warp stitcher declined (several contours, on-plane vertices, open / non-manifold
                           //       nodes, inconsistent winding, too large): the CTA stitcher takes them; count in totals[SHB_T_NDECL]
     uint32_t* dup_list;   // [G]   planes with two consecutive contour nodes closer than Path.merge_vertices' grid: the
                           //       merge pass takes them; count in totals[SHB_T_NDUP]
@@ -116,7 +116,7 @@ struct ShbDev {
 };
 
 enum { SHB_T_M = 0, SHB_T_BAD = 1, SHB_T_CAP = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
-       SHB_T_NCONT = 6, SHB_T_NPTS = 7, SHB_T_NDECL = 8, SHB_T_NDUP = 9 };
+       SHB_T_NCONT = 6, SHB_T_NPTS = 7, SHB_T_NDECL = 8, SHB_T_NDUP = 9, SHB_T_NDECL2 = 10 };
 
 // bytes of workspace the stitch kernel needs for a plane with n segments
 __host__ __device__ inline uint32_t shb_pow2_ge(uint32_t x) {
@@ -186,7 +186,8 @@ int shb_launch_scatter(const ShbDev& d, cudaStream_t st);
 int shb_launch_intersect(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_candidates(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
-int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t max_faces, size_t smem_budget, int n_sm, cudaStream_t st);
+int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t max_faces, size_t smem_budget, int n_sm, cudaStream_t st,
+                      cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join);
 int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t maxN, int n_sm, cudaStream_t st);
 int shb_launch_compact(const ShbDev& d, const uint32_t* ct_off, const uint32_t* pt_off,
                        double* pts_out, int64_t* ctpt_out, double* ctarea_out, cudaStream_t st);

@@ -2,9 +2,9 @@
 # Round-2 GPU check: parity tests, default bench, then stitch-kernel parameter sweeps (stage times only).
 tag=${1:-r2x}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/${tag}_pytest.txt
+python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/${tag}_pytest.txt
 cat gpurun_out/${tag}_pytest.txt
-python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+python bench.py --steps 10 --warmup 3 --no-cpu --no-sub --no-parity > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 tail -c 600 gpurun_out/${tag}_bench.err
 python - <<PY
 import json
