@@ -10,7 +10,8 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libshoulder_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("SHB_LIB") or Path(__file__).resolve().parent / "libshoulder_b200.so")      # SHB_LIB: experiments only
 
 # --- constants mirrored from include/shoulder_b200.h ---------------------------------------
 ABI_VERSION = 2

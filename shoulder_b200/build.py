@@ -42,7 +42,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not stale():
         return LIB
     extra = os.environ.get("SHB_NVCC_EXTRA", "").split()          # experiments only
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    out = os.environ.get("SHB_BUILD_OUT", str(LIB))                   # experiments only: a second library beside the product
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", out, *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)

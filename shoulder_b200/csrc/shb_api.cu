@@ -218,7 +218,11 @@ SHB_API int shb_init(int device) {
     CK(cudaStreamCreateWithFlags(&g.own, cudaStreamNonBlocking));
     g.stream = g.own;
     CK(cudaStreamCreateWithFlags(&g.copy, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g.aux, cudaStreamNonBlocking));
+    {   // highest priority: its few CTAs (declined planes) must get SM slots while the bulk launch still has thousands queued
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&g.aux, cudaStreamNonBlocking, hi));
+    }
     CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.sized, cudaEventDisableTiming));
@@ -841,13 +845,13 @@ SHB_API const void* shb_result_array(shb_result* r, int32_t which, int32_t sweep
             return r->h_pts + 2 * (size_t)r->h_pt_off[p0];
         case SHB_ARR_RADIAL: *dtype = r->esz == 4 ? SHB_DT_F32 : SHB_DT_F64; *ndim = 2; shape[1] = r->n_angles;
             shape[0] = (int64_t)sw.win_hi[SHB_A_RADIAL] - sw.win_lo[SHB_A_RADIAL];         // the rows of the sweep's window
-            if (shape[0] == 0 && !r->h_arr[SHB_A_RADIAL]) { fail(SHB_E_STATE, "sweep %d did not request the radial image", sweep); return nullptr; }
+            if (shape[0] == 0 && (sw.n_plane > 0 || !r->h_arr[SHB_A_RADIAL])) { fail(SHB_E_STATE, "sweep %d did not request the radial image", sweep); return nullptr; }
             return (const char*)r->h_arr[SHB_A_RADIAL] + sw.arr_off[SHB_A_RADIAL] * r->esz;
         default: {
             const int a = which - SHB_ARR_IXY;
             *dtype = r->esz == 4 ? SHB_DT_F32 : SHB_DT_F64; *ndim = 3; shape[1] = 2; shape[2] = (int64_t)N;
             shape[0] = (int64_t)sw.win_hi[a] - sw.win_lo[a];
-            if (shape[0] == 0 && !r->h_arr[a]) { fail(SHB_E_STATE, "sweep %d did not request profile array %d", sweep, a); return nullptr; }
+            if (shape[0] == 0 && (sw.n_plane > 0 || !r->h_arr[a])) { fail(SHB_E_STATE, "sweep %d did not request profile array %d", sweep, a); return nullptr; }
             return (const char*)r->h_arr[a] + sw.arr_off[a] * r->esz;
         }
     }
