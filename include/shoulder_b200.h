@@ -211,6 +211,42 @@ SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launch
 /* Number of kernels this library has launched since shb_init (bench.py's gpu_launches). */
 SHB_API int64_t shb_launch_count(void);
 
+/* ---- feature extraction on the polar stacks while they are in HBM ("next" row f3 of the scope table) --------------------
+ * The landmark code of the reference loops over the rows of two windows of the proximal sweep right after slice.py hands
+ * them over.  These calls run those loops on the device on the rows a result still holds (float64 runs only), for a list
+ * of sweeps at once; the outputs are small, so the stacks themselves need not be fetched.  Outputs are caller-owned host
+ * buffers, filled when the call returns.  rows = sum over the listed sweeps of their window of the array named below.
+ *
+ * shb_groove_features: bicipital_groove.py:94-156 on the itr_centered_start window (SHB_OUT_ITR_CENTERED_START): per row
+ *   Savitzky-Golay(10, 1), scipy.signal.find_peaks(height=-10, prominence=0.6, width=0.1), the 7 most prominent peaks and
+ *   their 9 features BEFORE the StandardScaler (radius, nearest and next-nearest angular distance to another peak, scaled z,
+ *   prominence, width, width height, distance to the canal axis, peak count / 7).
+ *     zs [rows] z of every row; canal_axes [n_sweep][2][3] Canal.axis() per sweep;
+ *     feat [rows][7][9], theta [rows][7], peak_index [rows][7] (sample index in the row, -1 = none), n_peaks [rows].
+ * shb_groove_points: bicipital_groove.py:190-238: per row the local minimum of the radius within +-ivar samples of
+ *   bg_theta[k] (k = position of the row's sweep in the list), as OBB-frame x, y, z (centroid added) + its theta.
+ *     points [rows][3], local_theta [rows].
+ * shb_neck_image: anatomic_neck.py:38-58 on the itr_start window (SHB_OUT_ITR_START): rows re-sampled on even theta,
+ *   rolled to bg_theta[k], MinMax-scaled per sweep -> image [rows][N] float32 (the UNet input); itr_shft (may be NULL)
+ *   [rows][2][N] float64 theta / r as rolled; minmax (may be NULL) [n_sweep][2]. */
+SHB_API int shb_groove_features(shb_result* result, int32_t n_sweep, const int32_t* sweeps, const double* zs, const double* canal_axes,
+                                double* feat, double* theta, int32_t* peak_index, int32_t* n_peaks);
+SHB_API int shb_groove_points(shb_result* result, int32_t n_sweep, const int32_t* sweeps, const double* bg_theta, int32_t ivar,
+                              const double* zs, double* points, double* local_theta);
+SHB_API int shb_neck_image(shb_result* result, int32_t n_sweep, const int32_t* sweeps, const double* bg_theta, float* image,
+                           double* itr_shft, double* minmax);
+
+/* Random forest of the groove detector on the device (bicipital_groove.py:174-181 opens rfc_bg3.onnx, an onnx-ml
+ * TreeEnsembleClassifier, through onnxruntime's CPU provider).  Nodes in one flat array, children after their parent;
+ * feature < 0 marks a leaf whose `weight` is added to the sample's score (BRANCH_LEQ: x[feature] <= value -> true child).
+ * score [n] = sum over trees = probability of class 1 for the binary forests skl2onnx writes. */
+typedef struct shb_forest shb_forest;
+SHB_API int shb_forest_create(int32_t n_nodes, int32_t n_trees, int32_t n_features, const uint32_t* root, const int32_t* feature,
+                              const float* value, const uint32_t* true_child, const uint32_t* false_child, const float* weight,
+                              shb_forest** out);
+SHB_API int shb_forest_predict(shb_forest* forest, const float* X, int32_t n, float* score);
+SHB_API int shb_forest_free(shb_forest* forest);
+
 SHB_API const char* shb_last_error(void);
 SHB_API int shb_abi_version(void);
 

@@ -35,6 +35,7 @@ EXPORTS = (
     "shb_sweep_batch",
     "shb_result_fetch", "shb_result_fetch_async", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
+    "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
 )
 
 
@@ -71,6 +72,12 @@ def load() -> C.CDLL:
     lib.shb_result_array.restype = C.c_void_p
     lib.shb_result_totals.argtypes = [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.shb_result_free.argtypes = [p]
+    lib.shb_groove_features.argtypes = [p, i32, p, p, p, p, p, p, p]
+    lib.shb_groove_points.argtypes = [p, i32, p, p, i32, p, p, p]
+    lib.shb_neck_image.argtypes = [p, i32, p, p, p, p, p]
+    lib.shb_forest_create.argtypes = [i32, i32, i32, p, p, p, p, p, p, pp]
+    lib.shb_forest_predict.argtypes = [p, p, i32, p]
+    lib.shb_forest_free.argtypes = [p]
     lib.shb_profile_enable.argtypes = [C.c_int]
     lib.shb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
     lib.shb_launch_count.restype = i64
@@ -183,6 +190,9 @@ class SweepResult:
         buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
         buf._shb_owner = self            # arr.base -> buf -> self keeps the pinned memory alive
         return np.frombuffer(buf, dtype=dtype).reshape(shp)   # a view, like the reference's cached arrays
+
+    def array_shape(self, which: int, sweep: int = 0):
+        return self.array(which, sweep).shape
 
     def window(self, which: int, sweep: int = 0):
         """(row_lo, row_hi) of the sweep's planes that array ``which`` covers in this result."""

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libshoulder_b200.so"
-SOURCES = ["shb_kernels.cu", "shb_api.cu"]
+SOURCES = ["shb_kernels.cu", "shb_features.cu", "shb_api.cu"]
 HEADERS = [CSRC / "shb_common.cuh", PKG.parent / "include" / "shoulder_b200.h"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",

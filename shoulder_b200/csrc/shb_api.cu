@@ -885,3 +885,197 @@ SHB_API int shb_sweep_batch(int32_t n_mesh, const double* verts, const int64_t* 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// f3: feature extraction on polar stacks that are still on the device (shb_features.cu)
+// ------------------------------------------------------------------------------------------
+extern "C" {
+int shb_launch_groove_features(const ShbRowSrc* src, int n_src, uint32_t rows, uint32_t maxN, const double* zs, double* feat, double* theta,
+                               int32_t* idx, int32_t* cnt, cudaStream_t st);
+int shb_launch_groove_points(const ShbRowSrc* src, int n_src, uint32_t rows, const double* zs, const double* bg, int ivar,
+                             const double* centroid, double* pts, double* local_theta, cudaStream_t st);
+int shb_launch_neck_image(const ShbRowSrc* src, int n_src, uint32_t rows, uint32_t N, const double* bg, double* vals, double* shft,
+                          unsigned long long* mm, float* image, double* mm_out, cudaStream_t st);
+int shb_launch_forest(const float* X, uint32_t n, uint32_t n_feat, uint32_t n_trees, const uint32_t* root, const int32_t* feature,
+                      const float* value, const uint32_t* tchild, const uint32_t* fchild, const float* weight, float* score, cudaStream_t st);
+}
+
+namespace {
+// rows of profile array `a` that the listed sweeps hold in the result, as device row sources; returns total rows or < 0
+int64_t row_sources(shb_result* r, int a, int32_t n_sw, const int32_t* sweeps, const double* zs, const double* canal_axes,
+                    std::vector<ShbRowSrc>& out, uint32_t& maxN) {
+    if (r->esz != 8) return fail(SHB_E_STATE, "feature extraction needs float64 profile arrays (run without SHB_OUT_F32)");
+    if (!r->d.prof[a]) return fail(SHB_E_STATE, "profile array %d was not computed by this run", a);
+    int64_t rows = 0;
+    maxN = 0;
+    for (int k = 0; k < n_sw; ++k) {
+        const int s = sweeps[k];
+        if (s < 0 || s >= (int)r->sweeps.size()) return fail(SHB_E_INVALID, "sweep %d out of range", s);
+        const ShbSweep& sw = r->sweeps[s];
+        ShbRowSrc q = {};
+        q.rows = sw.win_hi[a] - sw.win_lo[a];
+        if (q.rows == 0) return fail(SHB_E_STATE, "sweep %d holds no row of profile array %d", s, a);
+        q.N = sw.interp_num; q.out_row0 = (uint32_t)rows; q.plane0 = sw.plane_off + sw.win_lo[a];
+        q.base = reinterpret_cast<const double*>(r->d.prof[a]) + sw.arr_off[a];
+        if (zs) {      // sklearn MinMaxScaler over the rows' z (bicipital_groove.py:92): z * scale_ + min_
+            double lo = zs[rows], hi = zs[rows];
+            for (uint32_t i = 0; i < q.rows; ++i) { lo = std::min(lo, zs[rows + i]); hi = std::max(hi, zs[rows + i]); }
+            double range = hi - lo;
+            if (range == 0.0) range = 1.0;
+            q.z_scale = 1.0 / range; q.z_min = 0.0 - lo * q.z_scale;
+        }
+        if (canal_axes) {   // utils.unit_vector(axis[0], axis[1])
+            const double* ax = canal_axes + 6 * (size_t)k;
+            const double vx = ax[0] - ax[3], vy = ax[1] - ax[4], vz = ax[2] - ax[5];
+            const double nrm = std::sqrt(vx * vx + vy * vy + vz * vz);
+            q.cu[0] = vx / nrm; q.cu[1] = vy / nrm; q.cu[2] = vz / nrm;
+        }
+        maxN = std::max(maxN, q.N);
+        rows += q.rows;
+        out.push_back(q);
+    }
+    return rows;
+}
+}  // namespace
+
+struct shb_forest {
+    uint32_t n_nodes = 0, n_trees = 0, n_feat = 0;
+    uint32_t *root = nullptr, *tchild = nullptr, *fchild = nullptr; int32_t* feature = nullptr; float *value = nullptr, *weight = nullptr;
+};
+
+extern "C" {
+
+SHB_API int shb_groove_features(shb_result* r, int32_t n_sw, const int32_t* sweeps, const double* zs, const double* canal_axes,
+                                double* feat, double* theta, int32_t* peak_index, int32_t* n_peaks) {
+    SHB_ENTER;
+    if (!r || !sweeps || !zs || !canal_axes || !feat || !theta || !peak_index || !n_peaks || n_sw <= 0) return fail(SHB_E_INVALID, "null argument");
+    std::vector<ShbRowSrc> src; uint32_t maxN = 0;
+    const int64_t rows = row_sources(r, 5, n_sw, sweeps, zs, canal_axes, src, maxN);
+    if (rows < 0) return (int)rows;
+    if (maxN > 1024) return fail(SHB_E_CAPACITY, "interp_num %u > 1024", maxN);
+    cudaStream_t st = r->stream ? r->stream : g.stream;
+    if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
+    ShbRowSrc* d_src = nullptr; double *d_zs = nullptr, *d_feat = nullptr, *d_th = nullptr; int32_t *d_idx = nullptr, *d_cnt = nullptr;
+    CK(dalloc(&d_src, n_sw, st)); CK(dalloc(&d_zs, rows, st)); CK(dalloc(&d_feat, (size_t)rows * 63, st)); CK(dalloc(&d_th, (size_t)rows * 7, st));
+    CK(dalloc(&d_idx, (size_t)rows * 7, st)); CK(dalloc(&d_cnt, rows, st));
+    CK(cudaMemcpyAsync(d_src, src.data(), n_sw * sizeof(ShbRowSrc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_zs, zs, rows * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_feat, 0, (size_t)rows * 63 * sizeof(double), st)); CK(cudaMemsetAsync(d_th, 0, (size_t)rows * 7 * sizeof(double), st));
+    CK(cudaMemsetAsync(d_idx, 0xFF, (size_t)rows * 7 * sizeof(int32_t), st));
+    g.launches += shb_launch_groove_features(d_src, n_sw, (uint32_t)rows, maxN, d_zs, d_feat, d_th, d_idx, d_cnt, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(feat, d_feat, (size_t)rows * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(theta, d_th, (size_t)rows * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(peak_index, d_idx, (size_t)rows * 7 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_peaks, d_cnt, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dfree(d_src, st); dfree(d_zs, st); dfree(d_feat, st); dfree(d_th, st); dfree(d_idx, st); dfree(d_cnt, st);
+    return SHB_OK;
+}
+
+SHB_API int shb_groove_points(shb_result* r, int32_t n_sw, const int32_t* sweeps, const double* bg_theta, int32_t ivar, const double* zs,
+                              double* points, double* local_theta) {
+    SHB_ENTER;
+    if (!r || !sweeps || !bg_theta || !zs || !points || !local_theta || n_sw <= 0 || ivar < 1) return fail(SHB_E_INVALID, "bad argument");
+    std::vector<ShbRowSrc> src; uint32_t maxN = 0;
+    const int64_t rows = row_sources(r, 5, n_sw, sweeps, nullptr, nullptr, src, maxN);
+    if (rows < 0) return (int)rows;
+    cudaStream_t st = r->stream ? r->stream : g.stream;
+    if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
+    ShbRowSrc* d_src = nullptr; double *d_zs = nullptr, *d_bg = nullptr, *d_pts = nullptr, *d_lt = nullptr;
+    CK(dalloc(&d_src, n_sw, st)); CK(dalloc(&d_zs, rows, st)); CK(dalloc(&d_bg, n_sw, st)); CK(dalloc(&d_pts, (size_t)rows * 3, st)); CK(dalloc(&d_lt, rows, st));
+    CK(cudaMemcpyAsync(d_src, src.data(), n_sw * sizeof(ShbRowSrc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_zs, zs, rows * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_bg, bg_theta, n_sw * sizeof(double), cudaMemcpyHostToDevice, st));
+    g.launches += shb_launch_groove_points(d_src, n_sw, (uint32_t)rows, d_zs, d_bg, ivar, r->d.o_centroid, d_pts, d_lt, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(points, d_pts, (size_t)rows * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(local_theta, d_lt, rows * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dfree(d_src, st); dfree(d_zs, st); dfree(d_bg, st); dfree(d_pts, st); dfree(d_lt, st);
+    return SHB_OK;
+}
+
+SHB_API int shb_neck_image(shb_result* r, int32_t n_sw, const int32_t* sweeps, const double* bg_theta, float* image, double* itr_shft, double* minmax) {
+    SHB_ENTER;
+    if (!r || !sweeps || !bg_theta || !image || n_sw <= 0) return fail(SHB_E_INVALID, "bad argument");
+    std::vector<ShbRowSrc> src; uint32_t maxN = 0;
+    const int64_t rows = row_sources(r, 3, n_sw, sweeps, nullptr, nullptr, src, maxN);
+    if (rows < 0) return (int)rows;
+    for (auto& q : src) if (q.N != maxN || q.N < 3 || q.N > 1024) return fail(SHB_E_INVALID, "the sweeps of one image call must share interp_num (3..1024)");
+    cudaStream_t st = r->stream ? r->stream : g.stream;
+    if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
+    const size_t tot = (size_t)rows * maxN;
+    ShbRowSrc* d_src = nullptr; double *d_bg = nullptr, *d_vals = nullptr, *d_shft = nullptr, *d_mmo = nullptr; unsigned long long* d_mm = nullptr; float* d_img = nullptr;
+    CK(dalloc(&d_src, n_sw, st)); CK(dalloc(&d_bg, n_sw, st)); CK(dalloc(&d_vals, tot, st)); CK(dalloc(&d_mm, 2 * (size_t)n_sw, st));
+    CK(dalloc(&d_mmo, 2 * (size_t)n_sw, st)); CK(dalloc(&d_img, tot, st));
+    if (itr_shft) CK(dalloc(&d_shft, 2 * tot, st));
+    CK(cudaMemcpyAsync(d_src, src.data(), n_sw * sizeof(ShbRowSrc), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_bg, bg_theta, n_sw * sizeof(double), cudaMemcpyHostToDevice, st));
+    std::vector<unsigned long long> mm0(2 * (size_t)n_sw);
+    for (int k = 0; k < n_sw; ++k) { mm0[2 * k] = ~0ull; mm0[2 * k + 1] = 0ull; }
+    CK(cudaMemcpyAsync(d_mm, mm0.data(), mm0.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+    g.launches += shb_launch_neck_image(d_src, n_sw, (uint32_t)rows, maxN, d_bg, d_vals, d_shft, d_mm, d_img, d_mmo, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(image, d_img, tot * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (itr_shft) CK(cudaMemcpyAsync(itr_shft, d_shft, 2 * tot * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (minmax) CK(cudaMemcpyAsync(minmax, d_mmo, 2 * (size_t)n_sw * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dfree(d_src, st); dfree(d_bg, st); dfree(d_vals, st); dfree(d_mm, st); dfree(d_mmo, st); dfree(d_img, st); dfree(d_shft, st);
+    return SHB_OK;
+}
+
+SHB_API int shb_forest_create(int32_t n_nodes, int32_t n_trees, int32_t n_features, const uint32_t* root, const int32_t* feature,
+                              const float* value, const uint32_t* true_child, const uint32_t* false_child, const float* weight,
+                              shb_forest** out) {
+    SHB_ENTER;
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (!out || n_nodes <= 0 || n_trees <= 0 || n_features <= 0 || !root || !feature || !value || !true_child || !false_child || !weight)
+        return fail(SHB_E_INVALID, "bad argument");
+    for (int i = 0; i < n_nodes; ++i) {
+        if (feature[i] >= n_features) return fail(SHB_E_INVALID, "node %d tests feature %d of %d", i, feature[i], n_features);
+        if (feature[i] >= 0 && (true_child[i] >= (uint32_t)n_nodes || false_child[i] >= (uint32_t)n_nodes || true_child[i] <= (uint32_t)i ||
+                                false_child[i] <= (uint32_t)i))
+            return fail(SHB_E_INVALID, "node %d: children must follow their parent", i);       // guarantees that every walk ends
+    }
+    for (int t = 0; t < n_trees; ++t) if (root[t] >= (uint32_t)n_nodes) return fail(SHB_E_INVALID, "bad root");
+    cudaStream_t st = g.stream;
+    shb_forest* f = new shb_forest;
+    f->n_nodes = n_nodes; f->n_trees = n_trees; f->n_feat = n_features;
+    CK(dalloc(&f->root, n_trees, st)); CK(dalloc(&f->feature, n_nodes, st)); CK(dalloc(&f->value, n_nodes, st));
+    CK(dalloc(&f->tchild, n_nodes, st)); CK(dalloc(&f->fchild, n_nodes, st)); CK(dalloc(&f->weight, n_nodes, st));
+    CK(cudaMemcpyAsync(f->root, root, n_trees * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(f->feature, feature, n_nodes * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(f->value, value, n_nodes * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(f->tchild, true_child, n_nodes * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(f->fchild, false_child, n_nodes * 4, cudaMemcpyHostToDevice, st)); CK(cudaMemcpyAsync(f->weight, weight, n_nodes * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    *out = f;
+    return SHB_OK;
+}
+
+SHB_API int shb_forest_predict(shb_forest* f, const float* X, int32_t n, float* score) {
+    SHB_ENTER;
+    if (!f || !X || !score || n < 0) return fail(SHB_E_INVALID, "bad argument");
+    if (n == 0) return SHB_OK;
+    cudaStream_t st = g.stream;
+    float *dX = nullptr, *ds = nullptr;
+    CK(dalloc(&dX, (size_t)n * f->n_feat, st)); CK(dalloc(&ds, n, st));
+    CK(cudaMemcpyAsync(dX, X, (size_t)n * f->n_feat * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ds, 0, (size_t)n * 4, st));
+    g.launches += shb_launch_forest(dX, n, f->n_feat, f->n_trees, f->root, f->feature, f->value, f->tchild, f->fchild, f->weight, ds, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(score, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dfree(dX, st); dfree(ds, st);
+    return SHB_OK;
+}
+
+SHB_API int shb_forest_free(shb_forest* f) {
+    SHB_ENTER;
+    if (!f) return SHB_OK;
+    cudaStream_t st = g.stream;
+    dfree(f->root, st); dfree(f->feature, st); dfree(f->value, st); dfree(f->tchild, st); dfree(f->fchild, st); dfree(f->weight, st);
+    delete f;
+    return SHB_OK;
+}
+
+}  // extern "C"

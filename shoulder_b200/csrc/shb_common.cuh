@@ -115,6 +115,16 @@ struct ShbDev {
     uint32_t  debug;             // test hooks: bit 0 = radius image by the all-candidates path on every plane
 };
 
+// one sweep's window of a profile array, as the feature kernels (shb_features.cu) see it
+struct ShbRowSrc {
+    const double* base;        // first row: (rows, 2, N) float64
+    uint32_t rows, N;
+    uint32_t out_row0;         // first output row of this sweep in the concatenated outputs
+    uint32_t plane0;           // global plane index of the window's first row (centroids)
+    double z_scale, z_min;     // MinMaxScaler of the rows' z: z * z_scale + z_min
+    double cu[3];              // unit vector of the canal axis as Canal.axis() returns it (bicipital_groove.py:70)
+};
+
 enum { SHB_T_M = 0, SHB_T_BAD = 1, SHB_T_CAP = 2, SHB_T_S = 3, SHB_T_MAXN = 4, SHB_T_NBIG = 5,
        SHB_T_NCONT = 6, SHB_T_NPTS = 7, SHB_T_NDECL = 8, SHB_T_NDUP = 9, SHB_T_NDECL2 = 10 };
 

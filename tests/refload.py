@@ -120,6 +120,33 @@ def reference_modules():
     return _cache
 
 
+def load_extra(name: str):
+    """Further landmark modules of the reference, loaded on demand (their third-party imports are stubbed as above)."""
+    mods = reference_modules()
+    if name in mods:
+        return mods[name]
+    stubs = []
+    def need(modname, **attrs):
+        if modname not in sys.modules:
+            _stub(modname, **attrs)
+            stubs.append(modname)
+    need("plotly.graph_objects", Scatter3d=lambda **k: k, Mesh3d=lambda **k: k, Surface=object, Figure=object)
+    need("plotly", graph_objects=sys.modules["plotly.graph_objects"])
+    need("skspatial.objects", Line=_Line, Points=lambda a: np.asarray(a), Plane=object, Vector=object, Sphere=object)
+    need("skspatial", objects=sys.modules["skspatial.objects"])
+    if "onnxruntime" not in sys.modules:
+        sys.modules["onnxruntime"] = _OnnxStub("onnxruntime"); stubs.append("onnxruntime")
+    need("ellipse", LsqEllipse=object)
+    need("trimesh.geometry")
+    need("trimesh", Trimesh=object, geometry=sys.modules["trimesh.geometry"])
+    try:
+        mods[name] = _load(f"shoulder.humerus.{name}", REF / "humerus" / f"{name}.py")
+    finally:
+        for k in stubs:
+            sys.modules.pop(k, None)
+    return mods[name]
+
+
 class OracleMesh:
     """What ``Slices`` touches of ``obb.mesh``: ``bounds`` and ``section_multiplane`` — the latter answered by the
     oracle's restatement of trimesh (``oracle.section_multiplane``)."""

@@ -1,0 +1,123 @@
+"""Feature stage between slice.py's polar stacks and the landmark models (scope row f3), pinned to the reference's own
+code: ``tests/golden/refgroove_*.npz`` were made by running ``DeepGroove.points()`` and ``AnatomicNeck.points()`` of the
+reference unchanged (tests/golden/make_groove_vectors.py; trimesh answered by the oracle, onnxruntime by the ONNX reader).
+
+  CPU   oracle/groove.py (restatement with scipy / numpy) == those vectors; the vectors == a live run (build container)
+  GPU   shb_groove_features / shb_forest / shb_groove_points / shb_neck_image == those vectors (1e-5 budget of north_star;
+        discrete results — which samples are peaks, bg_theta, which sample is the local minimum — exact)
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import groove
+from shoulder_b200 import meshio
+
+import refload
+
+HERE = Path(__file__).resolve().parent
+GOLD = HERE / "golden"
+sys.path.insert(0, str(GOLD))
+import make_groove_vectors as mgv  # noqa: E402
+
+NAMES = mgv.NAMES
+needs_reference = pytest.mark.skipif(not refload.available(), reason="/root/reference is not on this host")
+
+
+def _bone(name):
+    g = np.load(GOLD / f"refgroove_{name}.npz")
+    ct = meshio.load_mesh(GOLD / "bones" / f"{name}.npz")
+    v, f = refload.exact_frame(ct.vertices, ct.faces, g["transform"])
+    zs = np.linspace(0.99 * v[:, 2].max(), float(g["neck_z"]), 600)            # ProximalSlices._zs, slice.py:248-253
+    return g, v, f, zs
+
+
+def _sorted_rows(X, theta, row):
+    """peaks of one stack row may come in any order (np.argpartition): sort by (row, theta)"""
+    k = np.lexsort((theta, row))
+    return X[k], theta[k], row[k]
+
+
+@needs_reference
+@pytest.mark.parametrize("name", NAMES[:1])
+def test_committed_groove_vectors_equal_a_live_run_of_the_reference(name):
+    g, v, f, zs = _bone(name)
+    live, _ = mgv.run_reference(v, f, g["transform"])
+    for key in ("X", "peak_theta", "proba", "groove_points_obb", "canal_axis"):
+        assert np.array_equal(live[key], g[key]), key
+    assert float(live["bg_theta"]) == float(g["bg_theta"])
+    assert np.array_equal(live["image"][::mgv.IMAGE_STRIDE], g["image_rows"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_groove_oracle_equals_the_reference_made_vectors(name):
+    g, v, f, zs = _bone(name)
+    orc = oracle.OracleSlices(v, f, zs, 512)
+    lo, hi = oracle.cutoff_window(600, (0.2, 0.75))
+    pol = orc.itr_centered_start[lo:hi]
+    ft = groove.groove_features(pol, zs[lo:hi], g["canal_axis"], 512)
+    assert ft["X"].shape == g["X"].shape and np.abs(ft["X"] - g["X"]).max() < 1e-12
+    assert np.array_equal(ft["peak_theta"], g["peak_theta"])
+    bg, _ = groove.groove_theta(ft["peak_theta"], g["proba"][:, 1])
+    assert bg == float(g["bg_theta"])
+    pts, _ = groove.groove_points(pol, ft["polar_0"], zs[lo:hi], orc.centroids[lo:hi], bg, 512)
+    assert np.array_equal(pts, g["groove_points_obb"])
+    lo2, hi2 = oracle.cutoff_window(600, (0.0, 0.852))
+    img, _, _ = groove.neck_image(orc.itr_start[lo2:hi2], bg)
+    assert np.array_equal(img.astype(np.float32)[::mgv.IMAGE_STRIDE], g["image_rows"])
+    assert abs(img.astype(np.float32).astype(np.float64).sum() - float(g["image_sum"])) < 1e-6
+
+
+@needs_reference
+def test_forest_reader_reproduces_the_reference_blob_semantics():
+    """oracle/onnx_forest.py on the reference's rfc_bg3.onnx: 40 trees, binary, scores in [0, 1], leaves sum to the class-1
+    fraction; the stored probabilities of the vectors come from it (no onnxruntime in the image to compare with)."""
+    from oracle.onnx_forest import Forest
+    fo = Forest(refload.REF / "humerus" / "models" / "rfc_bg3.onnx")
+    assert fo.n_trees == 40 and fo.n_classes == 2 and fo.binary_single
+    g = np.load(GOLD / "refgroove_humerus_left.npz")
+    p = fo.predict_proba(g["X"])
+    assert np.array_equal(p, g["proba"]) and (p >= 0).all() and np.allclose(p.sum(axis=1), 1.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_gpu_feature_stage_reproduces_the_reference_made_vectors(gpu_backend, name):
+    from shoulder_b200 import _lib, features
+    g, v, f, zs = _bone(name)
+    lo, hi = oracle.cutoff_window(600, (0.2, 0.75))
+    lo2, hi2 = oracle.cutoff_window(600, (0.0, 0.852))
+    zo = float(np.mean(zs))
+    req = [{_lib.OUT_ITR_START: (lo2, hi2), _lib.OUT_ITR_CENTERED_START: (lo, hi)}]
+    res = _lib.sweep_batch([(v, f)], [(0, zo, zs - zo, 512)], _lib.OUT_PLANE, 0, requests=req, lazy=True)
+    ft = features.groove_features(res, [0], [zs[lo:hi]], [g["canal_axis"]])[0]
+    # which samples are peaks, per row: exact; features within north_star's 1e-5
+    orc = oracle.OracleSlices(v, f, zs, 512)
+    ref = groove.groove_features(orc.itr_centered_start[lo:hi], zs[lo:hi], g["canal_axis"], 512)
+    assert np.array_equal(ft["n_peaks"], np.bincount(ref["peak_row"], minlength=hi - lo))
+    Xg, tg, rg = _sorted_rows(ft["X"], ft["peak_theta"], ft["peak_row"])
+    Xr, tr, rr = _sorted_rows(g["X"], g["peak_theta"], ref["peak_row"])
+    assert np.array_equal(rg, rr) and np.array_equal(tg, tr)
+    assert np.abs(Xg - Xr).max() < 1e-5 * max(1.0, np.abs(Xr).max())
+    # forest on the device == the ONNX semantics on the host; density arg-max == the reference's bg_theta
+    if (GOLD / "forest_rfc_bg3.npz").exists():
+        forest = features.Forest.from_arrays(np.load(GOLD / "forest_rfc_bg3.npz"))
+        k = np.lexsort((ft["peak_theta"], ft["peak_row"]))
+        proba = forest.predict_proba(ft["X"][k])
+        kr = np.lexsort((g["peak_theta"], ref["peak_row"]))
+        assert np.abs(proba - g["proba"][kr]).max() < 1e-6
+        bg = features.groove_theta(ft["peak_theta"][k], proba[:, 1])
+    else:
+        bg = features.groove_theta(g["peak_theta"], g["proba"][:, 1])
+    assert bg == float(g["bg_theta"])
+    pts, _ = features.groove_points(res, [0], [zs[lo:hi]], [bg], 512)[0]
+    assert np.abs(pts - g["groove_points_obb"]).max() < 1e-9 * np.abs(g["groove_points_obb"]).max()
+    img, (mn, mx), shft = features.neck_image(res, [0], [bg], want_shifted=True)[0]
+    assert img.shape == tuple(g["image_shape"]) and img.dtype == np.float32
+    assert np.abs(img[::mgv.IMAGE_STRIDE].astype(np.float64) - g["image_rows"]).max() < 1e-5
+    assert abs(img.astype(np.float64).sum() - float(g["image_sum"])) < 1e-5 * float(g["image_sum"])
+    _, shft_ref, _ = groove.neck_image(orc.itr_start[lo2:hi2], bg)
+    assert np.abs(shft - shft_ref).max() < 1e-9 * np.abs(shft_ref).max()
