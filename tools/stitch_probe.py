@@ -9,10 +9,10 @@ import bench
 from shoulder_b200 import _lib
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
-bones = int(sys.argv[2]) if len(sys.argv) > 2 else (1 if wl == "cfg3" else 32)
+bones = int(sys.argv[2]) if len(sys.argv) > 2 else (1 if wl.startswith("cfg3") else 32)
 _lib.init(0)
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream); _lib.set_stream(stream.cuda_stream)
-meshes, sweeps = bench.make_bones(wl, bones, 0, 8192 if wl == "cfg3" else 2048, 360)
+meshes, sweeps = bench.make_bones(wl, bones, 0, 8192 if wl.startswith("cfg3") else 2048, 360)
 packed = list(_lib._pack(meshes, sweeps))
 batch = _lib.SweepBatch(None, None, packed=packed)
 mask = _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_ITR_START | _lib.OUT_ITR_CENTERED_START | _lib.OUT_RADIAL
