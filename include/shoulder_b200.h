@@ -211,6 +211,23 @@ SHB_API int shb_profile_read(double stage_ms[SHB_N_STAGES], int64_t stage_launch
 /* Number of kernels this library has launched since shb_init (bench.py's gpu_launches). */
 SHB_API int64_t shb_launch_count(void);
 
+/* ---- resident meshes and single-plane sections ("next" row f1) ---------------------------------------------------------
+ * shb_mesh_create uploads one mesh (K0 conversion + face adjacency) and keeps it in HBM; verts / faces may be released
+ * when it returns.  shb_batch_create_on builds sweeps on it without an upload; shb_mesh_transform makes a second resident
+ * mesh under a 4x4 matrix on the device.  shb_section replaces Trimesh.section(plane_normal, plane_origin) — reference call
+ * sites mesh.py:95-99,158-161, surgical_neck.py:37-50, anatomic_neck.py:160-165, arthroplasty.py:71 — for ONE plane with
+ * any normal: the result holds plane records and the closed contours in the plane's own 2-D frame, and to_3d (16 doubles,
+ * row-major, may be NULL) maps (x, y, 0, 1) back to the mesh frame.  A mesh handle may be freed while batches / results
+ * made from it are alive. */
+typedef struct shb_mesh shb_mesh;
+SHB_API int shb_mesh_create(const double* verts, int64_t n_vert, const int64_t* faces, int64_t n_face, shb_mesh** out);
+SHB_API int shb_mesh_free(shb_mesh* mesh);
+SHB_API int shb_mesh_transform(shb_mesh* src, const double* to_2d, shb_mesh** out);
+SHB_API int shb_batch_create_on(shb_mesh* mesh, int32_t n_sweep, const double* z_orig, const double* heights,
+                                const int64_t* height_off, const int32_t* interp_num, shb_batch** out);
+SHB_API int shb_section(shb_mesh* mesh, const double* plane_normal, const double* plane_origin, uint32_t outputs_mask,
+                        double* to_3d, shb_result** out);
+
 /* ---- feature extraction on the polar stacks while they are in HBM ("next" row f3 of the scope table) --------------------
  * The landmark code of the reference loops over the rows of two windows of the proximal sweep right after slice.py hands
  * them over.  These calls run those loops on the device on the rows a result still holds (float64 runs only), for a list

@@ -31,6 +31,8 @@ from .trimesh_path import (  # noqa: F401
     mesh_plane,
     mesh_multiplane,
     section_multiplane,
+    section,
+    OraclePath3D,
     hashable_rows,
     float_to_int,
     rank_key,

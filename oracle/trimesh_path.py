@@ -308,7 +308,8 @@ def lines_to_path(segments_2d: np.ndarray, keys=None, merge: str = "hash", versi
     merge="topo": the GPU's rule — endpoints merge when they lie on the same mesh edge /
     vertex (``keys``); vertex id = rank of the kept coordinate's hash.  ``info['agree']`` says
     whether the two rules give the same graph on this plane."""
-    pts = np.asarray(segments_2d, dtype=np.float64).reshape(-1, 2)
+    segments_2d = np.asarray(segments_2d, dtype=np.float64)
+    pts = segments_2d.reshape(-1, segments_2d.shape[-1])           # 2 columns (section_multiplane) or 3 (Trimesh.section)
     h, packed = hashable_rows(pts, version)
     _, uidx, inv = np.unique(h, return_index=True, return_inverse=True)
     inv = inv.reshape(-1)
@@ -410,20 +411,23 @@ def process_path(vertices: np.ndarray, entities, version: str = "4"):
 
 
 def _hash_int_rows(q: np.ndarray, version: str = "4"):
-    """``hashable_rows`` on already-integer rows (see :func:`hashable_rows`)."""
-    threshold = 2 ** 31
+    """``hashable_rows`` on already-integer rows (see :func:`hashable_rows`).  Rows of D columns are packed into one
+    64-bit word when every value fits ``64 // D`` bits (32 for the 2-D paths of ``section_multiplane``; 21 for the 3-D
+    paths of ``Trimesh.section``, i.e. |coordinate| < 0.0105 mm — never on a bone, so 3-D rows are always void rows)."""
+    precision = 64 // q.shape[1]
+    threshold = 2 ** (precision - 1)
     if version == "4":
         if q.max() < threshold and q.min() > -threshold:
             bang = (q.T + (threshold + 1)).astype(np.uint64)
             h = np.zeros(len(q), dtype=np.uint64)
             for offset, col in enumerate(bang):
-                np.bitwise_xor(h, col << np.uint64(offset * 32), out=h)
+                np.bitwise_xor(h, col << np.uint64(offset * precision), out=h)
             return h, True
     else:
         if np.abs(q).max() < threshold:
             h = np.zeros(len(q), dtype=np.int64)
             for offset, col in enumerate(q.T):
-                np.bitwise_xor(h, col << (offset * 32), out=h)
+                np.bitwise_xor(h, col << (offset * precision), out=h)
             return h, True
     void = np.ascontiguousarray(q).view(np.dtype((np.void, q.dtype.itemsize * q.shape[1]))).reshape(-1)
     return void, False
@@ -593,6 +597,37 @@ class OraclePath2D:
                 if depth[j] == depth[i] + 1 and _point_in_ring(c.ring[0], p.ring):
                     total -= c.area
         return total
+
+
+class OraclePath3D:
+    """What ``Trimesh.section`` hands back (reference call sites mesh.py:95-99,158-161, surgical_neck.py:37-50,
+    anatomic_neck.py:160-165, arthroplasty.py:71): the 3-D segments of ``mesh_plane`` through ``load_path`` — row hashes
+    over THREE columns (always void rows: memcmp order), the same traversal, and ``discrete`` WITHOUT the counter-clockwise
+    normalisation of 2-D paths: a closed polyline runs from its start node towards the neighbour with the lower id."""
+
+    def __init__(self, vertices, entities, metadata=None, info=None):
+        self.vertices, self.entities, self.metadata, self.info = vertices, entities, metadata or {}, info or {}
+
+    @property
+    def discrete(self):
+        return [self.vertices[e] for e in self.entities]
+
+    @property
+    def bounds(self):
+        return np.array([self.vertices.min(axis=0), self.vertices.max(axis=0)])
+
+
+def section(vertices, faces, plane_normal, plane_origin, version="4", process=True):
+    """trimesh ``Trimesh.section(plane_normal, plane_origin)``; ``None`` when the plane misses the mesh."""
+    vertices = np.asarray(vertices, dtype=np.float64)
+    n = np.asarray(plane_normal, dtype=np.float64).reshape(3)
+    lines, fidx, keys, klass = mesh_plane(vertices, faces, np.asarray(plane_origin, dtype=np.float64).reshape(3), n)
+    if len(lines) == 0:
+        return None
+    verts, ents, info = lines_to_path(lines, None, merge="hash", version=version)
+    if process:
+        verts, ents, info["n_merged"] = process_path(verts, ents, version)
+    return OraclePath3D(verts, ents, metadata={"face_index": fidx}, info=info)
 
 
 def section_multiplane(vertices, faces, plane_origin, plane_normal, heights, merge="hash", version="4",

