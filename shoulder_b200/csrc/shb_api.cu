@@ -189,6 +189,9 @@ struct shb_result {
     cudaStream_t stream = nullptr;          // the stream the result was computed on; its device memory is freed there
     uint32_t W = 0;                         // capacity of the per-segment arrays
     ShbDev d = {};                          // device pointers owned by the result
+    // device memory of a run comes in four blocks carved by offset (not ~45 pool calls): scratch sized by the batch and
+    // scratch sized by the segment count (both released when the run is enqueued), and the two blocks the result keeps
+    void *blk_keep_a = nullptr, *blk_keep_b = nullptr, *blk_tmp_a = nullptr, *blk_tmp_b = nullptr;
     cudaEvent_t done = nullptr;             // recorded on the compute stream when the result's kernels are enqueued
     uint32_t* d_ct_off = nullptr; uint32_t* d_pt_off = nullptr;
     double* d_pts_c = nullptr; int64_t* d_ctpt_c = nullptr; double* d_ctarea_c = nullptr;
@@ -633,12 +636,7 @@ SHB_API int shb_result_free(shb_result* r) {
     if (r->pending) { cudaStreamSynchronize(g.copy); r->pending = false; }
     cudaStream_t st = r->stream ? r->stream : g.stream;      // the stream that computed it: frees are ordered behind its kernels
     ShbDev& d = r->d;
-    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
-    dfree(d.sort_cur, st); dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.cap_sorted, st); dfree(d.totals, st); dfree(d.totals64, st);
-    dfree(d.rec, st); dfree(d.hits, st); dfree(d.seg_off, st); dfree(d.big_list, st); dfree(d.meta, st);
-    dfree(d.o_nseg, st); dfree(d.o_nent, st); dfree(d.o_status, st); dfree(d.o_bounds, st); dfree(d.o_centroid, st);
-    dfree(d.o_area1, st); dfree(d.o_sel, st); dfree(d.face_index, st); dfree(d.segments, st); dfree(d.pts, st);
-    dfree(d.ct_start, st); dfree(d.ct_len, st); dfree(d.ct_area, st); dfree(d.decl_list, st); dfree(d.dup_list, st);
+    dfree(r->blk_keep_a, st); dfree(r->blk_keep_b, st); dfree(r->blk_tmp_a, st); dfree(r->blk_tmp_b, st);
     for (int a = 0; a < 6; ++a) if (d.prof[a]) { cudaFreeAsync(d.prof[a], st); d.prof[a] = nullptr; }
     if (d.radial) { cudaFreeAsync(d.radial, st); d.radial = nullptr; }
     dfree(d.scratch, st);
@@ -748,18 +746,32 @@ static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t o
         d.resample_order = b->rs_order; d.n_resample = b->n_rs;
     }
 
-    CK(dalloc(&d.item_lo, d.n_item, st)); CK(dalloc(&d.item_span, d.n_item, st)); CK(dalloc(&d.rec, d.n_item, st));
-    CK(dalloc(&d.inc, G, st)); CK(dalloc(&d.sort_off, G + 1, st)); CK(dalloc(&d.sort_cur, G, st)); CK(dalloc(&d.cnt, G, st));
     const size_t n_tiles = ((size_t)G + 4095) / 4096;
-    CK(dalloc(&d.scan_state, 4 * n_tiles + 4, st)); CK(dalloc(&d.dec, G + 1, st)); CK(dalloc(&d.cap_off, G + 1, st)); CK(dalloc(&d.cap_sorted, G, st));
-    CK(dalloc(&d.totals, 16, st)); CK(dalloc(&d.totals64, 2, st)); CK(dalloc(&d.seg_off, G + 1, st)); CK(dalloc(&d.big_list, G, st));
-    CK(dalloc(&d.meta, G, st)); CK(dalloc(&d.o_nseg, G, st)); CK(dalloc(&d.o_nent, G, st)); CK(dalloc(&d.o_status, G, st));
-    CK(dalloc(&d.o_bounds, 4 * (size_t)G, st)); CK(dalloc(&d.o_centroid, 2 * (size_t)G, st)); CK(dalloc(&d.o_area1, G, st));
-    CK(dalloc(&d.o_sel, 2 * (size_t)G, st)); CK(dalloc(&d.decl_list, 2 * (size_t)G, st)); CK(dalloc(&d.dup_list, G, st));
-    CK(cudaMemsetAsync(d.inc, 0, G * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(d.sort_cur, 0, G * sizeof(uint32_t), st)); CK(cudaMemsetAsync(d.dec, 0, ((size_t)G + 1) * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(d.totals, 0, 16 * sizeof(uint32_t), st));
-    CK(cudaMemsetAsync(d.scan_state, 0, (4 * n_tiles + 4) * sizeof(unsigned long long), st));
+    {
+        // one block of scratch and one block the result keeps, carved by offset; the counters that must start at zero
+        // lie together at the front of the scratch block and are cleared by ONE memset
+        struct Carve { size_t off = 0; size_t add(size_t bytes) { off = (off + 255) & ~(size_t)255; const size_t o = off; off += std::max<size_t>(bytes, 16); return o; } };
+        Carve t, k;
+        const size_t o_inc = t.add(G * 4), o_cur = t.add(G * 4), o_dec = t.add(((size_t)G + 1) * 4), o_scan = t.add((4 * n_tiles + 4) * 8);
+        const size_t zero_end = t.off;
+        const size_t o_lo = t.add((size_t)d.n_item * 4), o_span = t.add((size_t)d.n_item * 4), o_rec = t.add((size_t)d.n_item * 16),
+                     o_soff = t.add(((size_t)G + 1) * 4), o_cnt = t.add(G * 4), o_cap = t.add(((size_t)G + 1) * 4), o_caps = t.add(G * 4),
+                     o_big = t.add(G * 4), o_decl = t.add(2 * (size_t)G * 4), o_dup = t.add(G * 4);
+        const size_t k_tot = k.add(16 * 4), k_tot64 = k.add(2 * 8), k_seg = k.add(((size_t)G + 1) * 4), k_meta = k.add((size_t)G * sizeof(ShbPlaneMeta)),
+                     k_nseg = k.add(G * 4), k_nent = k.add(G * 4), k_stat = k.add(G * 4), k_bnd = k.add((size_t)G * 32), k_cen = k.add((size_t)G * 16),
+                     k_area = k.add((size_t)G * 8), k_sel = k.add((size_t)G * 8);
+        CK(dalloc_bytes(&r->blk_tmp_a, t.off, st)); CK(dalloc_bytes(&r->blk_keep_a, k.off, st));
+        unsigned char* T = (unsigned char*)r->blk_tmp_a; unsigned char* K = (unsigned char*)r->blk_keep_a;
+        d.inc = (uint32_t*)(T + o_inc); d.sort_cur = (uint32_t*)(T + o_cur); d.dec = (uint32_t*)(T + o_dec); d.scan_state = (unsigned long long*)(T + o_scan);
+        d.item_lo = (uint32_t*)(T + o_lo); d.item_span = (uint32_t*)(T + o_span); d.rec = (uint4*)(T + o_rec); d.sort_off = (uint32_t*)(T + o_soff);
+        d.cnt = (uint32_t*)(T + o_cnt); d.cap_off = (uint32_t*)(T + o_cap); d.cap_sorted = (uint32_t*)(T + o_caps); d.big_list = (uint32_t*)(T + o_big);
+        d.decl_list = (uint32_t*)(T + o_decl); d.dup_list = (uint32_t*)(T + o_dup);
+        d.totals = (uint32_t*)(K + k_tot); d.totals64 = (unsigned long long*)(K + k_tot64); d.seg_off = (uint32_t*)(K + k_seg);
+        d.meta = (ShbPlaneMeta*)(K + k_meta); d.o_nseg = (int32_t*)(K + k_nseg); d.o_nent = (int32_t*)(K + k_nent); d.o_status = (uint32_t*)(K + k_stat);
+        d.o_bounds = (double*)(K + k_bnd); d.o_centroid = (double*)(K + k_cen); d.o_area1 = (double*)(K + k_area); d.o_sel = (int32_t*)(K + k_sel);
+        CK(cudaMemsetAsync(T, 0, zero_end, st));
+        CK(cudaMemsetAsync(d.totals, 0, 16 * sizeof(uint32_t), st));
+    }
     CK(cudaMemcpyAsync(d.totals + SHB_T_BAD, b->d_bad, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));   // slot 1: bad-face flag
 
     // shared-memory capacities (leave headroom for static shared memory)
@@ -804,10 +816,19 @@ static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t o
     if (g.h_totals64[0] >= (1ull << 31)) return fail(SHB_E_CAPACITY, "%llu candidate segments in one batch; split it", g.h_totals64[0]);
     r->W = S;
     const uint32_t avgn = (uint32_t)(S / std::max<uint32_t>(G, 1u));     // mean segments per plane picks the CTA size
-    CK(dalloc(&d.hits, (size_t)S + 1, st));      // 16-byte records: every plane's list is a TMA-aligned run
     const bool want_seg = (outputs_mask & SHB_OUT_SEGMENTS) != 0;
-    CK(dalloc(&d.face_index, want_seg ? S : 1, st)); CK(dalloc(&d.segments, 4 * (size_t)S, st)); CK(dalloc(&d.pts, 4 * (size_t)S + 4, st));
-    CK(dalloc(&d.ct_start, S, st)); CK(dalloc(&d.ct_len, S, st)); CK(dalloc(&d.ct_area, S, st));
+    {
+        struct Carve { size_t off = 0; size_t add(size_t bytes) { off = (off + 255) & ~(size_t)255; const size_t o = off; off += std::max<size_t>(bytes, 16); return o; } };
+        Carve k;
+        const size_t k_fi = k.add((want_seg ? (size_t)S : 1) * 4), k_segm = k.add(32 * (size_t)S), k_pts = k.add(32 * (size_t)S + 64),
+                     k_cs = k.add((size_t)S * 4), k_cl = k.add((size_t)S * 4), k_ca = k.add((size_t)S * 8);
+        CK(dalloc_bytes(&r->blk_tmp_b, 16 * ((size_t)S + 1), st));      // 16-byte hit records: every plane's list is a TMA-aligned run
+        CK(dalloc_bytes(&r->blk_keep_b, k.off, st));
+        unsigned char* K = (unsigned char*)r->blk_keep_b;
+        d.hits = (uint4*)r->blk_tmp_b;
+        d.face_index = (int32_t*)(K + k_fi); d.segments = (double*)(K + k_segm); d.pts = (double*)(K + k_pts);
+        d.ct_start = (uint32_t*)(K + k_cs); d.ct_len = (uint32_t*)(K + k_cl); d.ct_area = (double*)(K + k_ca);
+    }
     bool any_prof = false;
     for (int a = 0; a < 6; ++a)
         if (r->arr_total[a]) { CK(dalloc_bytes(&d.prof[a], r->arr_total[a] * r->esz, st)); any_prof = true; }
@@ -838,9 +859,9 @@ static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t o
     if (any_prof) { StageTimer t(6, st); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)
-    dfree(d.item_lo, st); dfree(d.item_span, st); dfree(d.inc, st); dfree(d.sort_off, st); dfree(d.scan_state, st);
-    dfree(d.sort_cur, st); dfree(d.rec, st); dfree(d.big_list, st); dfree(d.hits, st); dfree(d.decl_list, st); dfree(d.dup_list, st);
-    dfree(d.cnt, st); dfree(d.dec, st); dfree(d.cap_off, st); dfree(d.cap_sorted, st); dfree(d.scratch, st);
+    dfree(r->blk_tmp_a, st); dfree(r->blk_tmp_b, st); dfree(d.scratch, st);
+    d.item_lo = d.item_span = d.inc = d.sort_off = d.sort_cur = d.cnt = d.dec = d.cap_off = d.cap_sorted = d.big_list = d.decl_list = d.dup_list = nullptr;
+    d.scan_state = nullptr; d.rec = nullptr; d.hits = nullptr;
     cudaFreeAsync(d_sw, st); d.sweep = nullptr;
     d.resample_order = nullptr;
     CK(cudaEventCreateWithFlags(&r->done, cudaEventDisableTiming));
