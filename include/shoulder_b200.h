@@ -228,6 +228,13 @@ SHB_API int shb_batch_create_on(shb_mesh* mesh, int32_t n_sweep, const double* z
 SHB_API int shb_section(shb_mesh* mesh, const double* plane_normal, const double* plane_origin, uint32_t outputs_mask,
                         double* to_3d, shb_result** out);
 
+/* Ray - mesh queries on a resident mesh ("next" row f4): trimesh mesh.ray.intersects_location as anatomic_neck.py:184-191,
+ * 217-224 calls it (four rays per bone).  Every triangle is tested with trimesh's plane / barycentric test (numpy backend);
+ * hits come in no particular order: (ray index, triangle index, location [3], distance along the ray).  n_hits receives the
+ * number of hits found; SHB_E_CAPACITY when it exceeds max_hits (the first max_hits are delivered). */
+SHB_API int shb_ray_cast(shb_mesh* mesh, int32_t n_ray, const double* origins, const double* directions, int32_t max_hits,
+                         int32_t* hit_ray, int32_t* hit_tri, double* hit_loc, double* hit_dist, int32_t* n_hits);
+
 /* ---- feature extraction on the polar stacks while they are in HBM ("next" row f3 of the scope table) --------------------
  * The landmark code of the reference loops over the rows of two windows of the proximal sweep right after slice.py hands
  * them over.  These calls run those loops on the device on the rows a result still holds (float64 runs only), for a list

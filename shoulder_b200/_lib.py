@@ -35,7 +35,7 @@ EXPORTS = (
     "shb_sweep_batch",
     "shb_result_fetch", "shb_result_fetch_async", "shb_result_array", "shb_result_totals", "shb_result_free", "shb_profile_enable",
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
-    "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section",
+    "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section", "shb_ray_cast",
     "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
 )
 
@@ -78,6 +78,7 @@ def load() -> C.CDLL:
     lib.shb_mesh_transform.argtypes = [p, p, pp]
     lib.shb_batch_create_on.argtypes = [p, i32, p, p, p, p, pp]
     lib.shb_section.argtypes = [p, p, p, u32, p, pp]
+    lib.shb_ray_cast.argtypes = [p, i32, p, p, i32, p, p, p, p, C.POINTER(i32)]
     lib.shb_groove_features.argtypes = [p, i32, p, p, p, p, p, p, p]
     lib.shb_groove_points.argtypes = [p, i32, p, p, i32, p, p, p]
     lib.shb_neck_image.argtypes = [p, i32, p, p, p, p, p]

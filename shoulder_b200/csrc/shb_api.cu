@@ -1231,6 +1231,39 @@ SHB_API int shb_neck_image(shb_result* r, int32_t n_sw, const int32_t* sweeps, c
     return SHB_OK;
 }
 
+extern "C" int shb_launch_ray_cast(const double4* vert, const int4* face, int64_t n_face, const double* org, const double* dir, int n_ray, int max_hits,
+                                   int32_t* hit_ray, int32_t* hit_tri, double* hit_loc, double* hit_dist, uint32_t* n_hits, cudaStream_t st);
+
+SHB_API int shb_ray_cast(shb_mesh* mesh, int32_t n_ray, const double* origins, const double* directions, int32_t max_hits,
+                         int32_t* hit_ray, int32_t* hit_tri, double* hit_loc, double* hit_dist, int32_t* n_hits) {
+    SHB_ENTER;
+    if (!mesh || !origins || !directions || !hit_ray || !hit_tri || !hit_loc || !n_hits || n_ray <= 0 || n_ray > 65535 || max_hits <= 0)
+        return fail(SHB_E_INVALID, "bad argument");
+    cudaStream_t st = g.stream;
+    if (mesh->stream != st && mesh->ready) CK(cudaStreamWaitEvent(st, mesh->ready, 0));
+    double *d_o = nullptr, *d_d = nullptr, *d_loc = nullptr, *d_dist = nullptr; int32_t *d_r = nullptr, *d_t = nullptr; uint32_t* d_n = nullptr;
+    CK(dalloc(&d_o, 3 * (size_t)n_ray, st)); CK(dalloc(&d_d, 3 * (size_t)n_ray, st)); CK(dalloc(&d_loc, 3 * (size_t)max_hits, st)); CK(dalloc(&d_dist, max_hits, st));
+    CK(dalloc(&d_r, max_hits, st)); CK(dalloc(&d_t, max_hits, st)); CK(dalloc(&d_n, 1, st));
+    CK(cudaMemcpyAsync(d_o, origins, 3 * (size_t)n_ray * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_d, directions, 3 * (size_t)n_ray * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_n, 0, sizeof(uint32_t), st));
+    g.launches += shb_launch_ray_cast(mesh->vert, mesh->face, mesh->nf, d_o, d_d, n_ray, max_hits, d_r, d_t, d_loc, d_dist, d_n, st);
+    CK(cudaGetLastError());
+    uint32_t n = 0;
+    CK(cudaMemcpyAsync(&n, d_n, sizeof n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint32_t keep = std::min<uint32_t>(n, (uint32_t)max_hits);
+    CK(cudaMemcpyAsync(hit_ray, d_r, keep * 4, cudaMemcpyDeviceToHost, st)); CK(cudaMemcpyAsync(hit_tri, d_t, keep * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hit_loc, d_loc, 3 * (size_t)keep * 8, cudaMemcpyDeviceToHost, st));
+    if (hit_dist) CK(cudaMemcpyAsync(hit_dist, d_dist, (size_t)keep * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (!mesh->last_use) CK(cudaEventCreateWithFlags(&mesh->last_use, cudaEventDisableTiming));
+    CK(cudaEventRecord(mesh->last_use, st));
+    dfree(d_o, st); dfree(d_d, st); dfree(d_loc, st); dfree(d_dist, st); dfree(d_r, st); dfree(d_t, st); dfree(d_n, st);
+    *n_hits = (int32_t)n;
+    return n > (uint32_t)max_hits ? fail(SHB_E_CAPACITY, "%u hits, room for %d", n, max_hits) : SHB_OK;
+}
+
 SHB_API int shb_forest_create(int32_t n_nodes, int32_t n_trees, int32_t n_features, const uint32_t* root, const int32_t* feature,
                               const float* value, const uint32_t* true_child, const uint32_t* false_child, const float* weight,
                               shb_forest** out) {

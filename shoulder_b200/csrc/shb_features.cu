@@ -328,7 +328,73 @@ __global__ void __launch_bounds__(256) k_forest(const float* __restrict__ X, uin
     atomicAdd(score + s, weight[cur]);
 }
 
+// ------------------------------------------------------------------------------------------
+// ray - mesh queries (scope row f4; anatomic_neck.py:184-191,217-224: mesh.ray.intersects_location, four rays per bone).
+// trimesh's numpy backend (ray_triangle_id): the ray meets the triangle's plane (face normal = unit cross product of the
+// first two edges; skipped when |direction . normal| <= 1e-5), the point is inside when its barycentric coordinates
+// (Cramer's rule, points_to_barycentric) lie in (-tol.zero, 1 + tol.zero), and only points at distance > -1e-6 along the
+// ray count.  trimesh prefilters candidates with an R-tree; the exact test is the same, so testing every triangle gives
+// the same set of hits.  One thread per (ray, triangle); hits are appended and sorted by (ray, triangle) on the host.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double4 shb_ldv4(const double4* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double shb_dot3(double ax, double ay, double az, double bx, double by, double bz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(ax, bx), __dmul_rn(ay, by)), __dmul_rn(az, bz));       // (a * b).sum(axis=1)
+}
+__global__ void __launch_bounds__(256) k_ray_cast(const double4* __restrict__ vert, const int4* __restrict__ face, int64_t n_face,
+                                                  const double* __restrict__ org, const double* __restrict__ dir, int n_ray,
+                                                  int max_hits, int32_t* __restrict__ hit_ray, int32_t* __restrict__ hit_tri,
+                                                  double* __restrict__ hit_loc, double* __restrict__ hit_dist, uint32_t* __restrict__ n_hits) {
+    const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int ray = blockIdx.y;
+    if (t >= n_face || ray >= n_ray) return;
+    const int4 f = __ldg(face + t);
+    const double4 A = shb_ldv4(vert + f.x), B = shb_ldv4(vert + f.y), C = shb_ldv4(vert + f.z);
+    const double e0x = __dsub_rn(B.x, A.x), e0y = __dsub_rn(B.y, A.y), e0z = __dsub_rn(B.z, A.z);
+    const double e1x = __dsub_rn(C.x, A.x), e1y = __dsub_rn(C.y, A.y), e1z = __dsub_rn(C.z, A.z);
+    // face normal: unitize(cross(e0, e1)); degenerate faces have none
+    double nx = __dsub_rn(__dmul_rn(e0y, e1z), __dmul_rn(e0z, e1y)), ny = __dsub_rn(__dmul_rn(e0z, e1x), __dmul_rn(e0x, e1z)),
+           nz = __dsub_rn(__dmul_rn(e0x, e1y), __dmul_rn(e0y, e1x));
+    const double nn = __dsqrt_rn(shb_dot3(nx, ny, nz, nx, ny, nz));
+    if (!(nn > 1e-13)) return;
+    nx = __ddiv_rn(nx, nn); ny = __ddiv_rn(ny, nn); nz = __ddiv_rn(nz, nn);
+    const double ox = org[3 * ray], oy = org[3 * ray + 1], oz = org[3 * ray + 2];
+    const double dx = dir[3 * ray], dy = dir[3 * ray + 1], dz = dir[3 * ray + 2];
+    const double p_ori = shb_dot3(__dsub_rn(A.x, ox), __dsub_rn(A.y, oy), __dsub_rn(A.z, oz), nx, ny, nz);
+    const double p_dir = shb_dot3(dx, dy, dz, nx, ny, nz);
+    if (!(fabs(p_dir) > 1e-5)) return;
+    const double dist = __ddiv_rn(p_ori, p_dir);
+    const double px = __dadd_rn(__dmul_rn(dx, dist), ox), py = __dadd_rn(__dmul_rn(dy, dist), oy), pz = __dadd_rn(__dmul_rn(dz, dist), oz);
+    const double wx = __dsub_rn(px, A.x), wy = __dsub_rn(py, A.y), wz = __dsub_rn(pz, A.z);
+    const double d00 = shb_dot3(e0x, e0y, e0z, e0x, e0y, e0z), d01 = shb_dot3(e0x, e0y, e0z, e1x, e1y, e1z), d02 = shb_dot3(e0x, e0y, e0z, wx, wy, wz),
+                 d11 = shb_dot3(e1x, e1y, e1z, e1x, e1y, e1z), d12 = shb_dot3(e1x, e1y, e1z, wx, wy, wz);
+    const double inv = __ddiv_rn(1.0, __dsub_rn(__dmul_rn(d00, d11), __dmul_rn(d01, d01)));
+    const double b2 = __dmul_rn(__dsub_rn(__dmul_rn(d00, d12), __dmul_rn(d01, d02)), inv);
+    const double b1 = __dmul_rn(__dsub_rn(__dmul_rn(d11, d02), __dmul_rn(d01, d12)), inv);
+    const double b0 = __dsub_rn(__dsub_rn(1.0, b1), b2);
+    const double tz = 1e-13;                                        // trimesh tol.zero
+    if (!(b0 > -tz && b1 > -tz && b2 > -tz && b0 < 1.0 + tz && b1 < 1.0 + tz && b2 < 1.0 + tz)) return;
+    const double fwd = shb_dot3(__dsub_rn(px, ox), __dsub_rn(py, oy), __dsub_rn(pz, oz), dx, dy, dz);
+    if (!(fwd > -1e-6)) return;
+    const uint32_t k = atomicAdd(n_hits, 1u);
+    if ((int)k < max_hits) {
+        hit_ray[k] = ray; hit_tri[k] = (int32_t)t;
+        hit_loc[3 * (size_t)k] = px; hit_loc[3 * (size_t)k + 1] = py; hit_loc[3 * (size_t)k + 2] = pz;
+        hit_dist[k] = fwd;
+    }
+}
+
 extern "C" {
+int shb_launch_ray_cast(const double4* vert, const int4* face, int64_t n_face, const double* org, const double* dir, int n_ray, int max_hits,
+                        int32_t* hit_ray, int32_t* hit_tri, double* hit_loc, double* hit_dist, uint32_t* n_hits, cudaStream_t st) {
+    if (!n_face || !n_ray) return 0;
+    dim3 grid((unsigned)((n_face + 255) / 256), (unsigned)n_ray);
+    k_ray_cast<<<grid, 256, 0, st>>>(vert, face, n_face, org, dir, n_ray, max_hits, hit_ray, hit_tri, hit_loc, hit_dist, n_hits);
+    return 1;
+}
 size_t shb_groove_smem_bytes(uint32_t N) { return 4 * (2 * (size_t)N + 64) * sizeof(double); }
 int shb_launch_groove_features(const ShbRowSrc* src, int n_src, uint32_t rows, uint32_t maxN, const double* zs, double* feat, double* theta,
                                int32_t* idx, int32_t* cnt, cudaStream_t st) {

@@ -86,6 +86,34 @@ class GpuPath3D:
         return self._p, self._to_3d
 
 
+class _Ray:
+    """``mesh.ray``: the one method the reference calls, ``intersects_location`` (anatomic_neck.py:184-191,217-224)."""
+
+    def __init__(self, mesh: "GpuMesh"):
+        self._mesh = mesh
+
+    def intersects_location(self, ray_origins, ray_directions, multiple_hits: bool = True):
+        o = np.ascontiguousarray(np.asarray(ray_origins, dtype=np.float64).reshape(-1, 3))
+        d = np.ascontiguousarray(np.asarray(ray_directions, dtype=np.float64).reshape(-1, 3))
+        cap = 64 * len(o)
+        while True:
+            ray = np.zeros(cap, dtype=np.int32); tri = np.zeros(cap, dtype=np.int32)
+            loc = np.zeros((cap, 3)); dist = np.zeros(cap); n = C.c_int32()
+            rc = _lib.load().shb_ray_cast(self._mesh.resident.h, len(o), _p(o), _p(d), cap, _p(ray), _p(tri), _p(loc), _p(dist), C.byref(n))
+            if rc == -4 and n.value > cap:                   # SHB_E_CAPACITY: more hits than room
+                cap = n.value
+                continue
+            _lib.check(rc)
+            break
+        k = n.value
+        order = np.lexsort((tri[:k], ray[:k]))               # device order is arbitrary: (ray, triangle) ascending
+        ray, tri, loc, dist = ray[:k][order], tri[:k][order], loc[:k][order], dist[:k][order]
+        if not multiple_hits and k:                          # nearest hit per ray
+            keep = np.array([np.nonzero(ray == r)[0][np.argmin(dist[ray == r])] for r in np.unique(ray)])
+            ray, tri, loc = ray[keep], tri[keep], loc[keep]
+        return loc, ray.astype(np.int64), tri.astype(np.int64)
+
+
 class GpuMesh:
     def __init__(self, vertices, faces):
         self.vertices = np.ascontiguousarray(vertices, dtype=np.float64)
@@ -93,6 +121,10 @@ class GpuMesh:
         self._handle = None
 
     # ---- the attributes of trimesh.Trimesh the path reads --------------------------------------
+    @property
+    def ray(self) -> _Ray:
+        return _Ray(self)
+
     @property
     def bounds(self) -> np.ndarray:
         return np.array([self.vertices.min(axis=0), self.vertices.max(axis=0)])

@@ -108,3 +108,25 @@ def test_tilted_plane_sections(gpu_backend, bone_obbs, seed):
     assert np.abs((p3.vertices - origin).dot(n)).max() < 1e-9
     d = np.abs(p3.vertices[:, None, :] - lifted[None, :, :]).sum(axis=2).min(axis=1)
     assert d.max() < 1e-8
+
+
+def test_ray_casts_match_the_restated_trimesh_test(gpu_backend, bone_obbs):
+    """anatomic_neck.py:184-191,217-224: rays from a point inside the head along +-normal -> where they leave the bone."""
+    from oracle import ray as oray
+    from shoulder_b200.mesh import GpuMesh
+    base = bone_obbs("humerus_left").mesh
+    m = GpuMesh(base.vertices, base.faces)
+    z = m.vertices[:, 2]
+    head = np.array([0.0, 0.0, 0.8 * z.max()])
+    rng = np.random.default_rng(4)
+    dirs = rng.normal(size=(12, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs = np.vstack([dirs, -dirs, [[0, 0, 1.0]], [[0, 0, -1.0]]])
+    orgs = np.repeat(head[None, :], len(dirs), axis=0) + rng.uniform(-1, 1, (len(dirs), 3))
+    loc, ray, tri = m.ray.intersects_location(orgs, dirs)
+    oloc, oray_i, otri = oray.intersects_location(m.vertices, m.faces, orgs, dirs)
+    k = np.lexsort((otri, oray_i))
+    assert np.array_equal(ray, oray_i[k]) and np.array_equal(tri, otri[k])        # which triangles every ray meets: exact
+    assert np.array_equal(loc, oloc[k])                                            # same arithmetic, same bits
+    assert len(np.unique(ray)) == len(dirs)                                        # from inside a closed bone every ray leaves it
+    one, r1, t1 = m.ray.intersects_location(orgs[:2], dirs[:2], multiple_hits=False)
+    assert len(one) == 2
