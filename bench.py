@@ -204,7 +204,7 @@ def workload_config(workload, bones, planes, interp, angles, world):
            "interp_num": interp if workload != "cfg4" else "100/500/512", "radial_angles": angles,
            "triangles_per_bone": {"cfg3": 519040, "cfg3l3": 2076160}.get(workload, 32440),
            "l2": "256 MiB buffer written between timed steps (L2 flush)",
-           "sharding": "by contiguous plane range of the one mesh, no collective" if workload.startswith("cfg3") else "by bone, no data-path collective"}
+           "sharding": "by plane range of the one mesh (blocks of 32 consecutive planes dealt round-robin), no collective" if workload.startswith("cfg3") else "by bone, no data-path collective"}
     if workload.startswith("cfg3") and world > 1:
         cfg["planes_per_gpu"] = planes // world
     return cfg
@@ -312,11 +312,12 @@ def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2
     nb = 1 if single else bones
     meshes, sweeps = make_bones(workload, nb, 0 if single else rank * nb, planes, interp)
     if single and world > 1:
-        # one large mesh: replicate it, shard the sweep by contiguous plane range (z_orig stays the full-list mean)
+        # one large mesh: replicate it, deal the sweep out in blocks of 32 consecutive planes (z_orig stays the full-list
+        # mean, so the scattered per-rank outputs equal the unsharded run bit for bit)
         from shoulder_b200 import sharding
         k, zo, h, n = sweeps[0]
-        lo, hi = sharding.shard_planes(len(h), rank, world)
-        sweeps = [(k, zo, h[lo:hi], n)]
+        idx = sharding.shard_planes_cyclic(len(h), rank, world)
+        sweeps = [(k, zo, np.ascontiguousarray(np.asarray(h)[idx]), n)]
     packed = list(_lib._pack(meshes, sweeps))
     pinned = [torch.from_numpy(a).pin_memory() for a in packed]         # the e2e leg copies from pinned memory
     packed_pinned = tuple(t.numpy() for t in pinned)

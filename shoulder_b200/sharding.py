@@ -38,3 +38,21 @@ def plane_shard_heights(zs: np.ndarray, rank: int, world: int):
     z_orig = float(np.mean(zs))
     lo, hi = shard_planes(len(zs), rank, world)
     return z_orig, (zs - z_orig)[lo:hi], (lo, hi)
+
+
+def shard_planes_cyclic(n_planes: int, rank: int, world: int, block: int = 32) -> np.ndarray:
+    """Plane indices of ``rank`` when the sweep is dealt out in blocks of ``block`` consecutive planes, round-robin.
+    The planes that cost many times the average (several contours: the condyles, the top of the head) sit at the two
+    ends of a bone; contiguous ranges hand them all to the first and the last rank (measured on config 3 at N = 8: 0.52 ms
+    per step against 0.24 ms of kernel time on rank 0), blocks spread them."""
+    idx = np.arange(n_planes, dtype=np.int64)
+    return idx[(idx // block) % world == rank]
+
+
+def plane_shard_heights_cyclic(zs: np.ndarray, rank: int, world: int, block: int = 32):
+    """As :func:`plane_shard_heights` for the block-cyclic deal; returns (z_orig, heights, plane indices).  Scatter the
+    per-rank outputs to ``out[indices]`` to rebuild the unsharded arrays (bit for bit: z_orig is the full-list mean)."""
+    zs = np.asarray(zs, dtype=np.float64)
+    z_orig = float(np.mean(zs))
+    idx = shard_planes_cyclic(len(zs), rank, world, block)
+    return z_orig, (zs - z_orig)[idx], idx

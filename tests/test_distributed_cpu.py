@@ -44,8 +44,16 @@ def _worker(rank, world, port, out):
     part = np.array([p.centroid for p in paths])
     parts = [None] * world
     dist.all_gather_object(parts, part)
+    # --- block-cyclic deal of the same sweep (what bench.py uses for one large mesh): scatter by index
+    z_orig2, h2, idx = sharding.plane_shard_heights_cyclic(zs, rank, world, block=2)
+    paths2 = oracle.section_multiplane(v, f, [0, 0, z_orig2], [0, 0, 1], h2)
+    cyc = [None] * world
+    dist.all_gather_object(cyc, (idx, np.array([p.centroid for p in paths2])))
     if rank == 0:
-        out.put((gathered, np.concatenate(parts)))
+        scattered = np.zeros((len(zs), 2))
+        for i, c in cyc:
+            scattered[i] = c
+        out.put((gathered, np.concatenate(parts), scattered))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -62,7 +70,7 @@ def test_world_size_2_gloo_sharding():
         if p.exitcode is None:
             p.kill()
         assert p.exitcode == 0, "gloo worker failed"
-    gathered, cat = out.get()
+    gathered, cat, scattered = out.get()
     ids = np.concatenate([g[0] for g in gathered])
     assert np.array_equal(np.sort(ids), np.arange(6))
     v, f = meshio.icosphere(2, 1.0, scale=(20.0, 30.0, 170.0))
@@ -74,3 +82,7 @@ def test_world_size_2_gloo_sharding():
     zs = np.linspace(150.0, -150.0, 11)
     whole = oracle.OracleSlices(v, f, zs, 16).centroids
     assert np.array_equal(cat, whole)
+    assert np.array_equal(scattered, whole)
+    for n, w in ((8192, 8), (100, 3)):
+        got = np.sort(np.concatenate([sharding.shard_planes_cyclic(n, r, w) for r in range(w)]))
+        assert np.array_equal(got, np.arange(n))

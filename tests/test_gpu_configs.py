@@ -178,7 +178,19 @@ def test_plane_range_shards_concatenate_to_the_unsharded_run():
             zo_r, h_r, (lo, hi) = sharding.plane_shard_heights(zs, rank, world)
             assert zo_r == zo
             parts.append(_lib.sweep_batch([(v, f)], [(0, zo_r, h_r, 128)], mask, 90))
-        for w in (_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_STATUS, _lib.ARR_CENTROID, _lib.ARR_BOUNDS, _lib.ARR_AREA1, _lib.ARR_IXY,
-                  _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START, _lib.ARR_RADIAL, _lib.ARR_POINTS, _lib.ARR_CONTOUR_AREA):
+        arrays = (_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_STATUS, _lib.ARR_CENTROID, _lib.ARR_BOUNDS, _lib.ARR_AREA1, _lib.ARR_IXY,
+                  _lib.ARR_ITR_START, _lib.ARR_ITR_CENTERED_START, _lib.ARR_RADIAL)
+        for w in arrays + (_lib.ARR_POINTS, _lib.ARR_CONTOUR_AREA):
             cat = np.concatenate([p.array(w) for p in parts])
             assert np.array_equal(cat, one.array(w), equal_nan=True), (world, w)
+        # the block-cyclic deal bench.py uses: per-plane arrays scattered back by index
+        cyc = []
+        for rank in range(world):
+            zo_r, h_r, idx = sharding.plane_shard_heights_cyclic(zs, rank, world, block=32)
+            cyc.append((idx, _lib.sweep_batch([(v, f)], [(0, zo_r, h_r, 128)], mask, 90)))
+        for w in arrays:
+            ref = one.array(w)
+            got = np.zeros_like(ref)
+            for idx, p in cyc:
+                got[idx] = p.array(w)
+            assert np.array_equal(got, ref, equal_nan=True), (world, w, "cyclic")
