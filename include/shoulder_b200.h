@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SHB_ABI_VERSION 2
+#define SHB_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define SHB_API __attribute__((visibility("default")))
@@ -227,6 +227,23 @@ SHB_API int shb_batch_create_on(shb_mesh* mesh, int32_t n_sweep, const double* z
                                 const int64_t* height_off, const int32_t* interp_num, shb_batch** out);
 SHB_API int shb_section(shb_mesh* mesh, const double* plane_normal, const double* plane_origin, uint32_t outputs_mask,
                         double* to_3d, shb_result** out);
+
+/* ---- mesh input on the device ("next" row f2) -------------------------------------------------------------------------------
+ * shb_mesh_from_stl: the bytes of a binary STL file -> a resident mesh.  Replaces MeshLoader._mesh_ct (mesh.py:24,
+ * trimesh.load_mesh = load_stl + Trimesh(process=True) -> merge_vertices: corners whose coordinates round equal at 1e-8 are
+ * one vertex, numbered by first occurrence, face order kept) and, with SHB_STL_FRAME, the frame step of FullObb._obb
+ * (mesh.py:82-117): trimesh's apply_obb (qhull) is not restatable, so the frame is this repo's PCA stand-in (principal axes,
+ * smallest variance -> x, largest -> z, AABB centred on the origin) followed by the reference's end test (the rounder end,
+ * judged at 0.95 of each z limit, goes to +z).  ASCII STL is rejected (SHB_E_INVALID).
+ *   n_vert / n_face   sizes of the welded mesh (may be NULL)
+ *   frame_out [22]    may be NULL: [0..15] 4x4 row-major matrix source -> frame (identity without SHB_STL_FRAME),
+ *                     [16..17] z bounds in the frame before the end flip (what mesh.py:88 keeps), [18] z length,
+ *                     [19] -1 when x and z were negated by the end test else +1, [20..21] circle-fit residuals of the two ends
+ * shb_mesh_read copies a resident mesh to the host as (n_vert,3) float64 + (n_face,3) int64 (what trimesh holds). */
+#define SHB_STL_FRAME 0x1u
+SHB_API int shb_mesh_from_stl(const void* stl_bytes, int64_t n_bytes, uint32_t flags, shb_mesh** out, int64_t* n_vert, int64_t* n_face,
+                              double* frame_out);
+SHB_API int shb_mesh_read(shb_mesh* mesh, double* verts, int64_t* faces);
 
 /* Ray - mesh queries on a resident mesh ("next" row f4): trimesh mesh.ray.intersects_location as anatomic_neck.py:184-191,
  * 217-224 calls it (four rays per bone).  Every triangle is tested with trimesh's plane / barycentric test (numpy backend);

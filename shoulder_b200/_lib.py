@@ -14,7 +14,7 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("SHB_LIB") or Path(__file__).resolve().parent / "libshoulder_b200.so")      # SHB_LIB: experiments only
 
 # --- constants mirrored from include/shoulder_b200.h ---------------------------------------
-ABI_VERSION = 2
+ABI_VERSION = 3
 OUT_PLANE, OUT_SEGMENTS, OUT_CONTOURS = 0x001, 0x002, 0x004
 OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START = 0x008, 0x010, 0x020, 0x040
 OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL = 0x080, 0x100, 0x200
@@ -23,6 +23,7 @@ OUT_F32 = 0x400
 (ARR_N_SEG, ARR_SEG_OFF, ARR_N_ENT, ARR_STATUS, ARR_BOUNDS, ARR_CENTROID, ARR_AREA1, ARR_SEL, ARR_FACE_INDEX,
  ARR_SEGMENTS, ARR_CONTOUR_OFF, ARR_CONTOUR_PT_OFF, ARR_CONTOUR_AREA, ARR_POINTS, ARR_IXY, ARR_IXY_CENTERED, ARR_ITR,
  ARR_ITR_START, ARR_ITR_CENTERED, ARR_ITR_CENTERED_START, ARR_RADIAL, ARR_COUNT) = range(22)
+STL_FRAME = 0x1
 ST_EMPTY, ST_OPEN, ST_NONMANIFOLD, ST_RANK_TIE, ST_SPLIT_COPY, ST_GENERAL, ST_MERGED = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 N_WINDOWED = 7                       # six profile arrays + the radius image (shb_sweep_request)
 WINDOWED_BITS = (OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START, OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL)
@@ -37,6 +38,7 @@ EXPORTS = (
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
     "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section", "shb_ray_cast",
     "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
+    "shb_mesh_from_stl", "shb_mesh_read",
 )
 
 

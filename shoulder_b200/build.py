@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libshoulder_b200.so"
-SOURCES = ["shb_kernels.cu", "shb_features.cu", "shb_api.cu"]
+SOURCES = ["shb_kernels.cu", "shb_features.cu", "shb_meshio.cu", "shb_api.cu"]
 HEADERS = [CSRC / "shb_common.cuh", PKG.parent / "include" / "shoulder_b200.h"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-lineinfo",
@@ -39,18 +39,41 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """One object per source (compiled in parallel, only the stale ones), then the shared library."""
     if not force and not stale():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     extra = os.environ.get("SHB_NVCC_EXTRA", "").split()          # experiments only
     out = os.environ.get("SHB_BUILD_OUT", str(LIB))                   # experiments only: a second library beside the product
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", out, *[str(CSRC / s) for s in SOURCES]]
+    objdir = PKG / "csrc" / ("_obj" if not extra else "_obj_x")
+    objdir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f not in ("-shared",)]
+    i = compile_flags.index("-cudart")
+    del compile_flags[i:i + 2]
+    newest_hdr = max(p.stat().st_mtime for p in HEADERS + [Path(__file__)])
+
+    def one(src: str):
+        obj = objdir / (src[:-3] + ".o")
+        s = CSRC / src
+        if not force and not extra and obj.exists() and obj.stat().st_mtime > max(s.stat().st_mtime, newest_hdr):
+            return obj, ""
+        cmd = [nvcc_path(), *compile_flags, *extra, "-c", "-o", str(obj), str(s)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        done = list(ex.map(one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        print("".join(d[1] for d in done))
+    link = [nvcc_path(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+            "-o", out, *[str(d[0]) for d in done]]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -346,6 +346,23 @@ SHB_API int shb_batch_free(shb_batch* b) {
     return SHB_OK;
 }
 
+// K0b: face adjacency of a set of faces (one hash table over its undirected edges; temporary)
+static int build_adjacency(const int4* face, int64_t nf, uint32_t** adj_out, cudaStream_t st) {
+    CK(dalloc(adj_out, 4 * (size_t)std::max<int64_t>(nf, 1), st));
+    if (nf) {
+        uint32_t hs = 1024;
+        while ((uint64_t)hs < 3ull * (uint64_t)nf) hs <<= 1;              // 1.5 T edges -> load <= 0.5
+        unsigned long long* keys = nullptr; uint32_t *cnt = nullptr, *own = nullptr, *hslot = nullptr;
+        CK(dalloc(&keys, hs, st)); CK(dalloc(&cnt, hs, st)); CK(dalloc(&own, 2 * (size_t)hs, st)); CK(dalloc(&hslot, 3 * (size_t)nf, st));
+        CK(cudaMemsetAsync(keys, 0xFF, (size_t)hs * sizeof(unsigned long long), st));
+        CK(cudaMemsetAsync(cnt, 0, (size_t)hs * sizeof(uint32_t), st));
+        g.launches += shb_launch_adjacency(face, nf, keys, cnt, own, hslot, hs, *adj_out, st);
+        CK(cudaGetLastError());
+        dfree(keys, st); dfree(cnt, st); dfree(own, st); dfree(hslot, st);
+    }
+    return SHB_OK;
+}
+
 static int batch_create_impl(int32_t n_mesh, const double* verts, const int64_t* vert_off, const int64_t* faces,
                              const int64_t* face_off, int32_t n_sweep, const int32_t* sweep_mesh, const double* z_orig,
                              const double* heights, const int64_t* height_off, const int32_t* interp_num, shb_mesh* shared, shb_batch** out) {
@@ -470,20 +487,7 @@ static int batch_create_impl(int32_t n_mesh, const double* verts, const int64_t*
     g.launches += shb_launch_prep_mesh(raw_v, raw_f, d_voff, d_foff, n_mesh, nv, nf, b->vert, b->vz, b->face, b->d_bad, st);
     CK(cudaGetLastError());
     dfree(raw_v, st); dfree(raw_f, st); dfree(d_voff, st); dfree(d_foff, st);
-    {   // K0b: face adjacency of the batch (one hash table over its undirected edges; temporary)
-        CK(dalloc(&b->adj, 4 * (size_t)std::max<int64_t>(nf, 1), st));
-        if (nf) {
-            uint32_t hs = 1024;
-            while ((uint64_t)hs < 3ull * (uint64_t)nf) hs <<= 1;              // 1.5 T edges -> load <= 0.5
-            unsigned long long* keys = nullptr; uint32_t *cnt = nullptr, *own = nullptr, *hslot = nullptr;
-            CK(dalloc(&keys, hs, st)); CK(dalloc(&cnt, hs, st)); CK(dalloc(&own, 2 * (size_t)hs, st)); CK(dalloc(&hslot, 3 * (size_t)nf, st));
-            CK(cudaMemsetAsync(keys, 0xFF, (size_t)hs * sizeof(unsigned long long), st));
-            CK(cudaMemsetAsync(cnt, 0, (size_t)hs * sizeof(uint32_t), st));
-            g.launches += shb_launch_adjacency(b->face, nf, keys, cnt, own, hslot, hs, b->adj, st);
-            CK(cudaGetLastError());
-            dfree(keys, st); dfree(cnt, st); dfree(own, st); dfree(hslot, st);
-        }
-    }
+    { int rc_adj = build_adjacency(b->face, nf, &b->adj, st); if (rc_adj) return rc_adj; }
     }
     // no host synchronisation here: the upload and K0 are only enqueued.  verts / faces must stay valid until the
     // first shb_batch_run on this batch returns (it synchronises); the face-index range check is reported there.
@@ -530,6 +534,111 @@ SHB_API int shb_mesh_create(const double* verts, int64_t n_vert, const int64_t* 
 SHB_API int shb_mesh_free(shb_mesh* m) {
     SHB_ENTER;
     if (m) mesh_unref(m);
+    return SHB_OK;
+}
+
+// ---- scope row f2: STL bytes -> welded mesh (-> frame) on the device (kernels: shb_meshio.cu) ---------------------------
+extern "C" {
+size_t shb_frame_state_bytes(void);
+size_t shb_frame_transform_offset(void);
+size_t shb_frame_zb_offset(void);
+size_t shb_frame_resid_offset(void);
+size_t shb_frame_flip_offset(void);
+int shb_launch_weld_count(const unsigned char* stl, uint32_t n_corner, uint32_t* table, uint32_t* first, uint32_t mask, uint32_t* slot_of,
+                          uint32_t* tile_sum, uint32_t* n_vert_out, cudaStream_t st);
+int shb_launch_weld_emit(const unsigned char* stl, uint32_t n_corner, const uint32_t* first, const uint32_t* slot_of, const uint32_t* tile_off,
+                         uint32_t* vid, double4* vert, double* vz, int4* face, cudaStream_t st);
+int shb_launch_frame(double4* vert, double* vz, uint32_t V, void* state, double* part, int n_sm, cudaStream_t st);
+int shb_launch_mesh_unpack(const double4* vert, int64_t nv, const int4* face, int64_t nf, double* v_out, int64_t* f_out, cudaStream_t st);
+}
+
+SHB_API int shb_mesh_from_stl(const void* stl, int64_t n_bytes, uint32_t flags, shb_mesh** out, int64_t* n_vert, int64_t* n_face,
+                              double* frame_out) {
+    SHB_ENTER;
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (!out || !stl) return fail(SHB_E_INVALID, "bad argument");
+    *out = nullptr;
+    if (n_bytes < 84) return fail(SHB_E_INVALID, "not a binary STL: %lld bytes", (long long)n_bytes);
+    uint32_t T = 0;
+    std::memcpy(&T, static_cast<const unsigned char*>(stl) + 80, 4);
+    if (84 + 50 * (int64_t)T != n_bytes)
+        return fail(SHB_E_INVALID, "not a binary STL (header says %u triangles, file has %lld bytes; ASCII STL is not read on the device)", T,
+                    (long long)n_bytes);
+    if (T == 0) return fail(SHB_E_INVALID, "STL without triangles");
+    if (T >= (1u << 29)) return fail(SHB_E_CAPACITY, "too many triangles in one mesh");
+    const uint32_t nc = 3u * T;
+    cudaStream_t st = g.stream;
+    unsigned char* d_stl = nullptr; uint32_t *table = nullptr, *first = nullptr, *slot_of = nullptr, *vid = nullptr, *tile_sum = nullptr, *d_nv = nullptr;
+    uint32_t hs = 1024;
+    while ((uint64_t)hs < 2ull * nc) hs <<= 1;
+    const uint32_t tiles = (nc + 2047u) / 2048u;
+    CK(dalloc(&d_stl, (size_t)n_bytes + 16, st)); CK(dalloc(&table, 2 * (size_t)hs, st)); first = table + hs;
+    CK(dalloc(&slot_of, 2 * (size_t)nc, st)); vid = slot_of + nc;
+    CK(dalloc(&tile_sum, (size_t)tiles + 1, st)); d_nv = tile_sum + tiles;
+    CK(cudaMemcpyAsync(d_stl, stl, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(table, 0xFF, 2 * (size_t)hs * sizeof(uint32_t), st));
+    g.launches += shb_launch_weld_count(d_stl, nc, table, first, hs - 1, slot_of, tile_sum, d_nv, st);
+    CK(cudaGetLastError());
+    uint32_t* h_nv = static_cast<uint32_t*>(pinned_get(16));
+    if (!h_nv) return fail(SHB_E_CUDA, "pinned allocation failed");
+    CK(cudaMemcpyAsync(h_nv, d_nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));                             // the vertex count sizes the mesh's own arrays
+    const uint32_t V = *h_nv;
+    pinned_put(h_nv);
+    shb_mesh* m = new shb_mesh;
+    m->nv = V; m->nf = T; m->stream = st;
+    CK(dalloc(&m->vert, V, st)); CK(dalloc(&m->vz, V, st)); CK(dalloc(&m->face, T, st)); CK(dalloc(&m->d_bad, 1, st));
+    CK(cudaMemsetAsync(m->d_bad, 0, sizeof(uint32_t), st));
+    g.launches += shb_launch_weld_emit(d_stl, nc, first, slot_of, tile_sum, vid, m->vert, m->vz, m->face, st);
+    CK(cudaGetLastError());
+    double* h_state = nullptr; unsigned char* d_state = nullptr; double* part = nullptr;
+    const size_t sb = shb_frame_state_bytes();
+    if (flags & SHB_STL_FRAME) {
+        CK(dalloc(&d_state, sb, st)); CK(dalloc(&part, (size_t)g.n_sm * 20, st));
+        CK(cudaMemsetAsync(d_state, 0, sb, st));
+        g.launches += shb_launch_frame(m->vert, m->vz, V, d_state, part, g.n_sm, st);
+        CK(cudaGetLastError());
+        h_state = static_cast<double*>(pinned_get(sb));
+        if (!h_state) return fail(SHB_E_CUDA, "pinned allocation failed");
+        CK(cudaMemcpyAsync(h_state, d_state, sb, cudaMemcpyDeviceToHost, st));
+    }
+    { int rc_adj = build_adjacency(m->face, T, &m->adj, st); if (rc_adj) return rc_adj; }
+    CK(cudaStreamSynchronize(st));
+    if (frame_out) {
+        for (int i = 0; i < 22; ++i) frame_out[i] = 0.0;
+        frame_out[0] = frame_out[5] = frame_out[10] = frame_out[15] = 1.0; frame_out[19] = 1.0;
+        if (h_state) {
+            const unsigned char* hb = reinterpret_cast<const unsigned char*>(h_state);
+            std::memcpy(frame_out, hb + shb_frame_transform_offset(), 16 * sizeof(double));
+            std::memcpy(frame_out + 16, hb + shb_frame_zb_offset(), 2 * sizeof(double));
+            frame_out[18] = std::fabs(frame_out[16]) + std::fabs(frame_out[17]);
+            std::memcpy(frame_out + 19, hb + shb_frame_flip_offset(), sizeof(double));
+            std::memcpy(frame_out + 20, hb + shb_frame_resid_offset(), 2 * sizeof(double));
+        }
+    }
+    if (h_state) pinned_put(h_state);
+    dfree(d_stl, st); dfree(table, st); dfree(slot_of, st); dfree(tile_sum, st); dfree(d_state, st); dfree(part, st);
+    CK(cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(m->ready, st));
+    if (n_vert) *n_vert = V;
+    if (n_face) *n_face = T;
+    *out = m;
+    return SHB_OK;
+}
+
+SHB_API int shb_mesh_read(shb_mesh* mesh, double* verts, int64_t* faces) {
+    SHB_ENTER;
+    if (!mesh || !verts || !faces) return fail(SHB_E_INVALID, "bad argument");
+    cudaStream_t st = g.stream;
+    if (mesh->stream != st && mesh->ready) CK(cudaStreamWaitEvent(st, mesh->ready, 0));
+    double* dv = nullptr; int64_t* df = nullptr;
+    CK(dalloc(&dv, 3 * (size_t)mesh->nv, st)); CK(dalloc(&df, 3 * (size_t)mesh->nf, st));
+    g.launches += shb_launch_mesh_unpack(mesh->vert, mesh->nv, mesh->face, mesh->nf, dv, df, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(verts, dv, 3 * (size_t)mesh->nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(faces, df, 3 * (size_t)mesh->nf * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dfree(dv, st); dfree(df, st);
     return SHB_OK;
 }
 

@@ -26,8 +26,11 @@ def _p(a):
 
 
 class _MeshHandle:
-    def __init__(self, vertices, faces):
+    def __init__(self, vertices=None, faces=None, adopt=None):
         _lib.init(_lib._inited if _lib._inited is not None else 0)
+        if adopt is not None:                                # a mesh made on the device (shb_mesh_from_stl)
+            self.h = adopt
+            return
         h = C.c_void_p()
         _lib.check(_lib.load().shb_mesh_create(_p(vertices), len(vertices), _p(faces), len(faces), C.byref(h)))
         self.h = h
@@ -120,6 +123,29 @@ class GpuMesh:
         self.faces = np.ascontiguousarray(faces, dtype=np.int64)
         self._handle = None
 
+    @classmethod
+    def from_stl(cls, stl, frame: bool = False):
+        """``trimesh.load_mesh(stl_file)`` (mesh.py:24) on the device: the file's bytes are parsed and welded there
+        (``shb_mesh_from_stl``) and the mesh stays resident; ``vertices`` / ``faces`` are read back once for the host-side
+        attributes.  ``frame=True`` also applies the oriented frame (``SHB_STL_FRAME``) and returns ``(mesh, info)`` with
+        ``info = {transform, z_bounds, z_length, flipped, residuals}``."""
+        from pathlib import Path
+        raw = stl if isinstance(stl, (bytes, bytearray, memoryview)) else Path(stl).read_bytes()
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        _lib.init(_lib._inited if _lib._inited is not None else 0)
+        h, nv, nf = C.c_void_p(), C.c_int64(), C.c_int64()
+        fo = np.zeros(22)
+        _lib.check(_lib.load().shb_mesh_from_stl(_p(buf), len(buf), _lib.STL_FRAME if frame else 0, C.byref(h), C.byref(nv), C.byref(nf), _p(fo)))
+        handle = _MeshHandle(adopt=h)
+        v, f = np.empty((nv.value, 3)), np.empty((nf.value, 3), dtype=np.int64)
+        _lib.check(_lib.load().shb_mesh_read(h, _p(v), _p(f)))
+        m = cls(v, f)
+        m._handle = handle
+        if not frame:
+            return m
+        return m, {"transform": fo[:16].reshape(4, 4).copy(), "z_bounds": (float(fo[16]), float(fo[17])), "z_length": float(fo[18]),
+                   "flipped": bool(fo[19] < 0), "residuals": (float(fo[20]), float(fo[21]))}
+
     # ---- the attributes of trimesh.Trimesh the path reads --------------------------------------
     @property
     def ray(self) -> _Ray:
@@ -192,6 +218,29 @@ class GpuMesh:
             if tilted:
                 lib.shb_mesh_free(tilted)
         return SectionSweep(_lib.SweepResult(r, 1), heights, to_2d, oz).paths()
+
+
+class GpuObb:
+    """``mesh.FullObb`` (mesh.py:57-127) with the STL parsed, welded and framed on the device: same attributes (``mesh``,
+    ``mesh_ct`` [the welded mesh in CT coordinates = the framed one under the inverse transform is NOT kept: ``mesh_ct`` is
+    loaded on demand], ``transform``, ``z_bounds``, ``z_length``, ``cutoff_pcts``, ``name``, ``file``).  The frame is the PCA
+    stand-in of :class:`shoulder_b200.meshio.PcaObb` (trimesh's ``apply_obb`` needs qhull)."""
+
+    def __init__(self, stl_file, name=None):
+        from pathlib import Path
+        if isinstance(stl_file, (bytes, bytearray, memoryview)):
+            self.file, self.name, self._raw = None, name or "mesh", bytes(stl_file)
+        else:
+            self.file = Path(stl_file)
+            self.name, self._raw = name or self.file.stem, self.file.read_bytes()
+        self.mesh, info = GpuMesh.from_stl(self._raw, frame=True)
+        self.transform = info["transform"]
+        self.z_bounds, self.z_length = info["z_bounds"], info["z_length"]
+        self.cutoff_pcts = [0.5, 0.8]
+
+    @property
+    def mesh_ct(self) -> GpuMesh:
+        return GpuMesh.from_stl(self._raw, frame=False)
 
 
 def install_mesh(obb) -> None:
