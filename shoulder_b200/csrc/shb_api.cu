@@ -902,6 +902,7 @@ static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t o
     if (getenv("SHB_DEBUG_RADIAL_GENERAL")) d.debug |= 1u;       // radius image by the all-candidates path on every plane
     if (getenv("SHB_DEBUG_MINRANK_ORDER")) d.debug |= 2u;        // contour order by minimum rank (no CPython-set emulation)
     if (getenv("SHB_DEBUG_NO_WARP_STITCH")) d.debug |= 4u;       // every plane through the CTA stitcher
+    if (getenv("SHB_DEBUG_ALLPAIRS_RANK")) d.debug |= 16u;       // node ranks of several-contour planes by the all-pairs loop
     d.stitch_order = getenv("SHB_DEBUG_NO_PERMUTE") ? nullptr : b->stitch_order;
     // K1 sizes everything downstream: the candidate triangles per plane (an upper bound of the hits that is exact
     // except on planes through vertices) are published as soon as the bucket histograms are scanned, and the host

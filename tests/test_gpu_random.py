@@ -63,3 +63,28 @@ def test_scene_of_blobs(gpu_backend, seed):
     zs = np.linspace(np.percentile(z, 80), np.percentile(z, 20), 30)
     rep = compare_sweep(v, f, zs, 48, n_angles=36, expect_all_closed=False)
     assert rep["contours"] >= 4 * len(zs)
+
+
+def test_bucketed_and_all_pairs_node_ranks_agree(gpu_backend, monkeypatch):
+    """The node ids behind the contour order come from a bucketed ranking on large planes and from an all-pairs count on
+    small ones (or when the shared scratch is short): one scene, both ways, identical results — and the oracle again."""
+    from shoulder_b200 import _lib
+    rng = np.random.default_rng(77)
+    vs, fs, off = [], [], 0
+    for k in range(9):
+        v, f = lumpy(900 + k, 4)                                # 5,120 faces each: several hundred segments per plane
+        v = 0.35 * (v - v.mean(axis=0)) + np.array([rng.uniform(-60, 60), rng.uniform(-60, 60), rng.uniform(-2, 2)])
+        vs.append(v); fs.append(f + off); off += len(v)
+    v, f = np.vstack(vs), np.vstack(fs)
+    z = v[:, 2]
+    zs = np.linspace(np.percentile(z, 70), np.percentile(z, 30), 12)
+    mask = _lib.OUT_PLANE | _lib.OUT_CONTOURS
+    a = _lib.sweep_batch([(v, f)], [(0, float(zs.mean()), zs - zs.mean(), 16)], mask)
+    assert a.array(_lib.ARR_N_SEG).min() >= 256                 # large enough for the bucketed path
+    monkeypatch.setenv("SHB_DEBUG_ALLPAIRS_RANK", "1")
+    b = _lib.sweep_batch([(v, f)], [(0, float(zs.mean()), zs - zs.mean(), 16)], mask)
+    monkeypatch.delenv("SHB_DEBUG_ALLPAIRS_RANK")
+    for w in (_lib.ARR_CONTOUR_OFF, _lib.ARR_CONTOUR_PT_OFF, _lib.ARR_POINTS, _lib.ARR_CONTOUR_AREA, _lib.ARR_STATUS):
+        assert np.array_equal(a.array(w), b.array(w))
+    rep = compare_sweep(v, f, zs, 16, expect_all_closed=False)
+    assert rep["contours"] >= 4 * len(zs)
