@@ -368,6 +368,26 @@ def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2
     ms = sum(a.elapsed_time(b) for a, b in ev)
     stages = {n: v for n, v in _lib.profile_read(reset=True).items() if n in heavy}      # measured live, inside the timed region
     _lib.profile_enable(False)
+    # the same step with SHB_OUT_F32 (polar forms and ray distances computed and stored in float32, north_star's 1e-5 budget;
+    # the theta-min roll stays a float64 decision): reported beside the float64 headline, never instead of it
+    f32 = None
+    if f32_leg:
+        m32 = mask | _lib.OUT_F32
+        for _ in range(3):
+            batch.run(m32, angles, requests).close()
+        torch.cuda.synchronize()
+        _lib.profile_enable(True, stages=heavy)
+        _lib.profile_read(reset=True)
+        ev32 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev32:
+            flush.fill_(1)
+            a.record(stream)
+            r = batch.run(m32, angles, requests)
+            b.record(stream)
+            r.close()
+        torch.cuda.synchronize()
+        f32 = {"ms": sum(a.elapsed_time(b) for a, b in ev32), "stages": {n: v[0] / steps for n, v in _lib.profile_read(reset=True).items() if n in heavy}}
+        _lib.profile_enable(False)
     batch.close()
 
     # ---------------- end-to-end leg (public host call) -----------------------------------
@@ -472,6 +492,14 @@ def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2
                 "call": f"shoulder_b200._lib.sweep_batch_pipelined, {len(chunks)} group(s) of bones"},
         "gpu_launches": int(launches),
     }
+    if f32 is not None:
+        ms32 = gpu.reduce([f32["ms"]])[0]
+        c32 = dict(c, esz=4)
+        rs32 = f32["stages"].get("resample", 0.0)
+        rec["f32"] = {"value": total_planes * steps / (ms32 * 1e-3), "unit": "planes/s", "ms_per_step": ms32 / steps,
+                      "stage_ms_per_step": f32["stages"],
+                      "resample_frac": (stage_alg_bytes("resample", c32) / (rs32 * 1e-3) / 1e9 / peak) if rs32 > 0 else None,
+                      "note": "device-resident leg with SHB_OUT_F32: float32 polar forms / ray distances (1e-5 budget of north_star), float64 contours and roll decision"}
     if e2e32_s is not None:
         rec["e2e_f32"] = {"value": total_planes * steps / (e2e32_ms_max * 1e-3), "unit": "planes/s",
                           "ms_per_step": e2e32_ms_max / steps, "note": "same call with SHB_OUT_F32 (float32 profile arrays)"}
@@ -525,6 +553,45 @@ def parity_block(gpu: Gpu, meshes, sweeps, mask, angles, max_planes=2048):
     return out
 
 
+def encode_stl(vertices, faces) -> bytes:
+    """(V,3), (T,3) -> bytes of a binary STL (float32 corners): the input of the f2 record."""
+    rec = np.zeros(len(faces), dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+    rec["v"] = np.asarray(vertices, dtype=np.float32)[np.asarray(faces)]
+    return b"\0" * 80 + np.uint32(len(faces)).tobytes() + rec.tobytes()
+
+
+def stl_record(gpu: Gpu, bones: int):
+    """Scope row f2: bones/s from STL BYTES to a welded, framed, HBM-resident mesh (shb_mesh_from_stl: H2D of the file,
+    parse, weld, PCA frame, end test, face adjacency, D2H of the welded arrays for the host-side attributes), beside the
+    host path the other configs use to build their inputs (numpy parse + weld + PCA frame)."""
+    from shoulder_b200 import meshio
+    from shoulder_b200.mesh import GpuMesh
+    bases = [meshio.load_mesh(ROOT / "tests" / "golden" / "bones" / f"{n}.npz") for n in NAMES]
+    raws = []
+    for i in range(bones):
+        m = meshio.synthetic_bone(bases[i % 4], gpu.rank * bones + i)
+        raws.append(encode_stl(m.vertices, m.faces))
+    for r in raws[:4]:
+        GpuMesh.from_stl(r, frame=True)
+    gpu.barrier()
+    t0 = time.perf_counter()
+    for r in raws:
+        GpuMesh.from_stl(r, frame=True)
+    gpu.torch.cuda.synchronize()
+    dt = gpu.reduce([time.perf_counter() - t0])[0]
+    t1 = time.perf_counter()
+    nh = min(bones, 8)
+    for r in raws[:nh]:
+        n_t = int(np.frombuffer(r, dtype="<u4", count=1, offset=80)[0])
+        rec = np.frombuffer(r, dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]), count=n_t, offset=84)
+        meshio.PcaObb(meshio.Mesh(*meshio.weld(np.array(rec["v"], dtype=np.float32))))
+    th = (time.perf_counter() - t1) / nh
+    return {"value": bones * gpu.world / dt, "unit": "bones/s", "ms_per_bone": 1e3 * dt / bones, "bones_per_gpu": bones,
+            "stl_bytes_per_bone": int(np.mean([len(r) for r in raws])),
+            "host_numpy_ms_per_bone": 1e3 * th, "host_sample": f"{nh} bones, one core",
+            "call": "shoulder_b200.mesh.GpuMesh.from_stl(bytes, frame=True) -> shb_mesh_from_stl + shb_mesh_read, one bone per call"}
+
+
 def traffic_from_profiles(workload, dom):
     """ncu --set full DRAM bytes of the dominant kernel, from the committed capture of this very command (labelled:
     it is NOT measured in this run — a bench number is never taken under ncu)."""
@@ -557,6 +624,10 @@ def run_ours(args, rank, world, local_rank):
                 subs[name] = r
             except Exception as e:          # a sub-record must not take the headline down
                 subs[name] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            subs["f2_stl"] = stl_record(gpu, args.bones)
+        except Exception as e:
+            subs["f2_stl"] = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if gpu.dist is not None:
             gpu.dist.destroy_process_group()
@@ -584,7 +655,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": rec["scaling"], "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": rec["config"], "bones_per_sec": rec["bones_per_sec"],
         "segments_per_step_per_gpu": rec["segments_per_step_per_gpu"], "contours_per_step_per_gpu": rec["contours_per_step_per_gpu"],
-        "roofline": rec["roofline"], "cpu_baseline": cpu, "e2e": rec["e2e"], "e2e_f32": rec.get("e2e_f32"),
+        "roofline": rec["roofline"], "cpu_baseline": cpu, "e2e": rec["e2e"], "f32": rec.get("f32"), "e2e_f32": rec.get("e2e_f32"),
         "gpu_launches": rec["gpu_launches"], "clocks": clocks, "parity": parity, "configs": subs,
     }
     print(json.dumps(line), flush=True)

@@ -15,5 +15,5 @@ for f in ("gpurun_out/${tag}_n${N}.json", "gpurun_out/${tag}_cfg4x128_n${N}.json
         print(f, "unreadable", e); continue
     print(f, "value", round(r["value"] / 1e6, 2), "M planes/s", round(r["ms_per_step"], 3), "ms; e2e", round(r["e2e"]["value"] / 1e6, 2), "M planes/s", round(r["e2e"]["ms_per_step"], 2), "ms; bones/s", round(r["bones_per_sec"]), round(r["e2e"]["bones_per_sec"]))
     for k, v in (r.get("configs") or {}).items():
-        print("   ", k, v.get("error") or (round(v["value"] / 1e6, 2), round(v["ms_per_step"], 3), "e2e", round(v["e2e"]["ms_per_step"], 2), "bones/s", round(v["bones_per_sec"]), round(v["e2e"]["bones_per_sec"])))
+        print("   ", k, v.get("error") or ((round(v["value"] / 1e6, 2), round(v["ms_per_step"], 3), "e2e", round(v["e2e"]["ms_per_step"], 2), "bones/s", round(v["bones_per_sec"]), round(v["e2e"]["bones_per_sec"])) if "e2e" in v else v))
 PY
