@@ -25,7 +25,7 @@ def _face_xor(fi):
 
 
 @pytest.mark.parametrize("name", NAMES)
-def test_oracle_reproduces_golden(name):
+def test_oracle_reproduces_its_own_frozen_outputs(name):          # regression pin of the restatement, not a reference vector
     g, m = _load(name)
     s = oracle.OracleSlices(m.vertices, m.faces, g["zs"], g["ixy"].shape[2])
     assert np.array_equal([len(p.metadata["face_index"]) for p in s.paths], g["n_seg"])
@@ -37,7 +37,7 @@ def test_oracle_reproduces_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
-def test_gpu_reproduces_golden(gpu_backend, name):
+def test_gpu_reproduces_the_frozen_oracle_outputs(gpu_backend, name):   # regression pin, not a reference vector
     from shoulder_b200 import _lib
     from helpers import run_gpu
     g, m = _load(name)
