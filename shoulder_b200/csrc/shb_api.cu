@@ -50,7 +50,7 @@ struct Ctx {
     cudaStream_t own = nullptr, stream = nullptr;
     cudaStream_t copy = nullptr;           // device->host copies run here so they overlap the next batch's kernels
     cudaStream_t aux = nullptr;            // the declined planes of the first part of a stitch launch run here, beside the bulk
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_mid = nullptr;
     cudaEvent_t sized = nullptr;           // recorded behind the size publication of a run
     int64_t launches = 0;
     uint32_t profile = 0;                  // bit s: stage s is timed
@@ -255,6 +255,7 @@ SHB_API int shb_init(int device) {
     }
     CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_mid, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&g.sized, cudaEventDisableTiming));
     // a private pool: its "never release on its own" threshold must not leak into other users of cudaMallocAsync
     cudaMemPoolProps props = {};
@@ -965,7 +966,7 @@ static int batch_run_impl(shb_batch* b, const shb_sweep_request* req, uint32_t o
 
     { StageTimer t(3, st); t.stop(shb_launch_intersect(d, st)); }
     { StageTimer t(4, st); t.stop(shb_launch_scan_counts(d, st)); }
-    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, b->max_faces, budget, g.n_sm, st, g.aux, g.ev_fork, g.ev_join)); }
+    { StageTimer t(5, st); t.stop(shb_launch_stitch(d, maxcand, avgn, b->max_faces, budget, g.n_sm, st, g.aux, g.ev_fork, g.ev_join, g.ev_mid, b->n_sweep > b->n_mesh)); }
     if (any_prof) { StageTimer t(6, st); t.stop(shb_launch_resample(d, maxcand, avgn, b->max_interp, g.n_sm, st)); }
     CK(cudaGetLastError());
     // stage scratch is dead once the kernels above are enqueued (stream ordered)

@@ -197,7 +197,7 @@ int shb_launch_intersect(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_candidates(const ShbDev& d, cudaStream_t st);
 int shb_launch_scan_counts(const ShbDev& d, cudaStream_t st);
 int shb_launch_stitch(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t max_faces, size_t smem_budget, int n_sm, cudaStream_t st,
-                      cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join);
+                      cudaStream_t aux, cudaEvent_t ev_fork, cudaEvent_t ev_join, cudaEvent_t ev_mid, bool partial_sweeps);
 int shb_launch_resample(const ShbDev& d, uint32_t maxcand, uint32_t avgn, uint32_t maxN, int n_sm, cudaStream_t st);
 int shb_launch_compact(const ShbDev& d, const uint32_t* ct_off, const uint32_t* pt_off,
                        double* pts_out, int64_t* ctpt_out, double* ctarea_out, cudaStream_t st);
