@@ -566,7 +566,7 @@ SHB_API int shb_mesh_from_stl(const void* stl, int64_t n_bytes, uint32_t flags, 
         return fail(SHB_E_INVALID, "not a binary STL (header says %u triangles, file has %lld bytes; ASCII STL is not read on the device)", T,
                     (long long)n_bytes);
     if (T == 0) return fail(SHB_E_INVALID, "STL without triangles");
-    if (T >= (1u << 29)) return fail(SHB_E_CAPACITY, "too many triangles in one mesh");
+    if (T >= (1u << 28)) return fail(SHB_E_CAPACITY, "too many triangles in one mesh");      // 6 T table slots must fit 32 bits
     const uint32_t nc = 3u * T;
     cudaStream_t st = g.stream;
     unsigned char* d_stl = nullptr; uint32_t *table = nullptr, *first = nullptr, *slot_of = nullptr, *vid = nullptr, *tile_sum = nullptr, *d_nv = nullptr;

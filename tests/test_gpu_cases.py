@@ -351,3 +351,31 @@ def test_path_merge_vertices_behind_both_stitchers(gpu_backend):
     f2 = np.vstack([f, f + len(v)])
     rep2 = compare_sweep(v2, f2, zs, 64, n_angles=36, expect_all_closed=False)
     assert len(rep2["merged_planes"]) >= 3 and rep2["contours"] > len(zs)
+
+
+def test_calls_from_another_host_thread(gpu_backend):
+    """CUDA's current device is per host thread: an entry point called from a thread that never saw shb_init must still
+    run on the library's device and streams (device guard at every entry point)."""
+    import threading
+    v, f = meshio.icosphere(3, 1.0, scale=(20.0, 30.0, 40.0))
+    zs = np.linspace(-35.0, 35.0, 40)
+    mask = _lib.OUT_PLANE | _lib.OUT_IXY | _lib.OUT_CONTOURS
+    ref = run_gpu(v, f, zs, 64, mask)
+    out = {}
+
+    def work():
+        try:
+            r = run_gpu(v, f, zs, 64, mask)
+            out["ixy"], out["pts"] = r.array(_lib.ARR_IXY).copy(), r.array(_lib.ARR_POINTS).copy()
+            r.close()
+        except Exception as e:          # surfaced in the main thread
+            out["err"] = e
+
+    ts = [threading.Thread(target=work) for _ in range(2)]
+    ts[0].start(); ts[0].join()
+    assert "err" not in out, out.get("err")
+    assert np.array_equal(out["ixy"], ref.array(_lib.ARR_IXY)) and np.array_equal(out["pts"], ref.array(_lib.ARR_POINTS))
+    ts[1].start()                        # a second thread while the main thread keeps calling
+    again = run_gpu(v, f, zs, 64, mask)
+    ts[1].join()
+    assert "err" not in out and np.array_equal(again.array(_lib.ARR_IXY), ref.array(_lib.ARR_IXY))
