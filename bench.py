@@ -8,7 +8,7 @@ A "step" is one pass of the whole hot path (bucket -> intersect -> stitch -> res
 over one batch of synthetic bones.  Headline workload = BASELINE.json configs[1]: the reference's
 ``humerus_left`` test bone under the config-4 jitter, 2,048 planes along the shaft axis per bone,
 outlines resampled to 360 points + the 360-ray radius image, ``--bones`` bones per step per GPU.
-The same line carries sub-records for the other BASELINE configs (``configs``: cfg3_L2 = 519,040 triangles,
+The same line carries sub-records for the other BASELINE configs (``configs``: cfg5_landmark_front_end, f2_stl, cfg3_L2 = 519,040 triangles,
 cfg3_L3 = 2,076,160 triangles, 8,192 planes each, sharded by plane range when N > 1; cfg4 = jittered test bones x the
 three default sweeps with the consumers' row windows, sharded by bone) and a ``parity`` block: one bone of the timed
 batch against the oracle, outside the timed region.
@@ -592,6 +592,70 @@ def stl_record(gpu: Gpu, bones: int):
             "call": "shoulder_b200.mesh.GpuMesh.from_stl(bytes, frame=True) -> shb_mesh_from_stl + shb_mesh_read, one bone per call"}
 
 
+def landmark_record(gpu: Gpu, bones: int, steps: int):
+    """BASELINE configs[4] as far as the checkout allows: the front end of the landmark pipeline on a batch, host buffers
+    in, landmark-model inputs out.  Per step: the three default sweeps of every bone with the consumers' windows
+    (shb_batch_run_req; the polar stacks stay in HBM), plane records to the host, canal axis per bone from the Full
+    sweep's centroids (canal.py:40-85: a line fit, host numpy), then on the device the groove feature rows
+    (bicipital_groove.py:94-156), the random forest rfc_bg3 (:174-181), on the host the density arg-max (:184-188), and on
+    the device the groove points (:190-238) and the 512-wide float32 neck image (anatomic_neck.py:38-58) the UNet would read
+    (the UNet blobs themselves are not in the checkout)."""
+    from shoulder_b200 import _lib, features
+    fx = ROOT / "tests" / "golden" / "forest_rfc_bg3.npz"
+    if not fx.exists():
+        return {"error": "forest fixture missing"}
+    forest = features.Forest.from_arrays(np.load(fx))
+    meshes, sweeps = make_bones("cfg4", bones, gpu.rank * bones, 0, 0)
+    req = consumer_requests(sweeps)
+    packed = tuple(gpu.torch.from_numpy(a).pin_memory().numpy() for a in _lib._pack(meshes, sweeps))
+    full = [3 * b for b in range(bones)]
+    prox = [3 * b + 2 for b in range(bones)]
+    zs_of = lambda s: np.asarray(sweeps[s][2]) + sweeps[s][1]
+    win_g = [(int((1 - 0.75) * 600), int((1 - 0.2) * 600))] * bones            # itr_centered_start rows (bicipital_groove.py:161)
+    zs_g = [zs_of(s)[lo:hi] for s, (lo, hi) in zip(prox, win_g)]
+
+    z_full = [zs_of(s) for s in full]
+    c_lo, c_hi = int((1 - 0.75) * 200), int((1 - 0.35) * 200)
+    half = np.array([0.55 * (abs(z[0]) + abs(z[-1])) / 2 for z in z_full])
+
+    def step(count=False):
+        res = _lib.sweep_batch(None, None, _lib.OUT_PLANE, 0, packed=packed, lazy=True, requests=req)
+        # canal.py:40-85 for every bone at once: centroids((0.35, 0.75)) of the Full sweep + z -> best-fit line (mean + first
+        # right singular vector, what scikit-spatial's Line.best_fit computes)
+        cz = np.stack([np.c_[res.array(_lib.ARR_CENTROID, s)[c_lo:c_hi], z_full[b][c_lo:c_hi]] for b, s in enumerate(full)])
+        mid = cz.mean(axis=1, keepdims=True)
+        dirn = np.linalg.svd(cz - mid)[2][:, 0, :]
+        dirn = np.where(dirn[:, -1:] < 0, -dirn, dirn)
+        axes = np.stack([mid[:, 0] + dirn * half[:, None], mid[:, 0] - dirn * half[:, None]], axis=1)
+        ft = features.groove_features(res, prox, zs_g, axes)
+        cuts = np.cumsum([0] + [len(f["X"]) for f in ft])
+        proba = forest.predict_proba(np.vstack([f["X"] for f in ft]))           # one forest launch for the whole batch
+        bg = features.groove_theta_batch([f["peak_theta"] for f in ft], [proba[a:b, 1] for a, b in zip(cuts[:-1], cuts[1:])])
+        pts = features.groove_points(res, prox, zs_g, bg, 512)
+        imgs = features.neck_image(res, prox, bg)
+        out_bytes = 0
+        if count:
+            out_bytes = sum(i[0].nbytes for i in imgs) + sum(p[0].nbytes + p[1].nbytes for p in pts) + sum(f["raw"].nbytes + f["peak_theta"].nbytes for f in ft)
+            out_bytes += 76 * sum(len(sw[2]) for sw in sweeps)                   # plane records
+        res.close()
+        return out_bytes, float(np.mean(bg))
+
+    for _ in range(2):
+        d2h, chk = step(True)
+    gpu.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    gpu.torch.cuda.synchronize()
+    dt = gpu.reduce([time.perf_counter() - t0])[0]
+    forest.close()
+    return {"value": bones * gpu.world * steps / dt, "unit": "bones/s", "ms_per_step": 1e3 * dt / steps, "bones_per_gpu": bones, "steps": steps,
+            "h2d_bytes_per_step": int(sum(a.nbytes for a in packed)), "d2h_bytes_per_bone": d2h / bones,
+            "delivers": "per bone: plane records of the three sweeps, canal axis, groove feature rows (<= 330 x 7 x 9) + forest probabilities, "
+                        "groove angle, 330 groove points, the 512 x 512 float32 neck image",
+            "note": "host buffers in, landmark-model inputs out; the polar stacks (4.2 + 2.7 MB per bone) never cross PCIe; mean groove angle %.6f" % chk}
+
+
 def traffic_from_profiles(workload, dom):
     """ncu --set full DRAM bytes of the dominant kernel, from the committed capture of this very command (labelled:
     it is NOT measured in this run — a bench number is never taken under ncu)."""
@@ -624,6 +688,10 @@ def run_ours(args, rank, world, local_rank):
                 subs[name] = r
             except Exception as e:          # a sub-record must not take the headline down
                 subs[name] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            subs["cfg5_landmark_front_end"] = landmark_record(gpu, args.bones, max(3, min(args.steps, 5)))
+        except Exception as e:
+            subs["cfg5_landmark_front_end"] = {"error": f"{type(e).__name__}: {e}"}
         try:
             subs["f2_stl"] = stl_record(gpu, args.bones)
         except Exception as e:

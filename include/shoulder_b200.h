@@ -202,6 +202,12 @@ SHB_API int shb_result_free(shb_result* result);
  * calls.  shb_trim() waits for outstanding work and hands everything that is idle back to the driver / OS. */
 SHB_API int shb_trim(void);
 
+/* Page-locked host memory from the library's cache, for the caller-owned output buffers of the calls below (shb_neck_image,
+ * shb_groove_features, shb_ray_cast, shb_mesh_read ...): a device->host copy into it runs at PCIe speed, into pageable memory at
+ * a fraction of it.  shb_host_free hands the block back to the cache (shb_trim releases idle blocks to the OS). */
+SHB_API int shb_host_alloc(int64_t bytes, void** out);
+SHB_API int shb_host_free(void* p);
+
 /* Per-stage CUDA-event timing of shb_batch_run (one event pair per timed stage, ~3 us of device time each).
  * on = 0: off; 1: every stage; otherwise a mask, bit (s + 1) = time stage s (e.g. 2 << 5 | 2 << 6: stitch and resample). */
 #define SHB_N_STAGES 7
@@ -287,6 +293,12 @@ SHB_API int shb_forest_create(int32_t n_nodes, int32_t n_trees, int32_t n_featur
                               shb_forest** out);
 SHB_API int shb_forest_predict(shb_forest* forest, const float* X, int32_t n, float* score);
 SHB_API int shb_forest_free(shb_forest* forest);
+
+/* The groove angle of each of n_set bones (bicipital_groove.py:184-188): peaks off[k] .. off[k+1] belong to bone k; those with
+ * proba1 > threshold (the reference uses 0.4) enter a linear-kernel density of bandwidth 1 evaluated on np.linspace(-pi, pi, 1024);
+ * bg_theta [n_set] receives the arg-max angle (first maximum, like np.argmax), density_max [n_set] (may be NULL) its value. */
+SHB_API int shb_groove_theta(int32_t n_set, const int64_t* off, const double* peak_theta, const float* proba1, float threshold,
+                             double* bg_theta, double* density_max);
 
 SHB_API const char* shb_last_error(void);
 SHB_API int shb_abi_version(void);

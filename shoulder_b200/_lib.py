@@ -38,7 +38,7 @@ EXPORTS = (
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
     "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section", "shb_ray_cast",
     "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
-    "shb_mesh_from_stl", "shb_mesh_read",
+    "shb_mesh_from_stl", "shb_mesh_read", "shb_groove_theta", "shb_host_alloc", "shb_host_free",
 )
 
 
@@ -98,6 +98,34 @@ def load() -> C.CDLL:
         raise BackendError("libshoulder_b200.so ABI version mismatch; rebuild")
     _lib = lib
     return lib
+
+
+class _PinnedBlock:
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        check(load().shb_host_alloc(int(nbytes), C.byref(p)))
+        self.ptr = p.value
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                load().shb_host_free(C.c_void_p(self.ptr))
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """Uninitialised numpy array in page-locked memory of the library's cache (``shb_host_alloc``): the output buffers of
+    the feature / mesh calls, so that their device->host copies run at PCIe speed.  Returned to the cache when the array
+    (and every view of it) is gone."""
+    init(_inited if _inited is not None else 0)
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64)) * dt.itemsize
+    blk = _PinnedBlock(max(n, 16))
+    buf = (C.c_char * max(n, 1)).from_address(blk.ptr)
+    buf._blk = blk                                  # the numpy array keeps `buf` as its base, `buf` keeps the block
+    return np.frombuffer(buf, dtype=dt, count=n // dt.itemsize).reshape(shape)
 
 
 def check(rc: int) -> None:

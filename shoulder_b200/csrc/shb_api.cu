@@ -297,6 +297,20 @@ SHB_API int shb_trim(void) {
     return SHB_OK;
 }
 
+SHB_API int shb_host_alloc(int64_t bytes, void** out) {
+    SHB_ENTER;
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (!out || bytes < 0) return fail(SHB_E_INVALID, "bad argument");
+    *out = pinned_get((size_t)bytes);
+    if (!*out) return fail(SHB_E_CUDA, "page-locked allocation of %lld bytes failed", (long long)bytes);
+    return SHB_OK;
+}
+SHB_API int shb_host_free(void* p) {
+    SHB_ENTER;
+    if (p) pinned_put(p);
+    return SHB_OK;
+}
+
 SHB_API int shb_profile_enable(int on) {
     SHB_ENTER;
     g.profile = on == 0 ? 0u : (on == 1 ? (1u << SHB_N_STAGES) - 1u : ((uint32_t)on >> 1) & ((1u << SHB_N_STAGES) - 1u));
@@ -1416,6 +1430,36 @@ SHB_API int shb_forest_predict(shb_forest* f, const float* X, int32_t n, float* 
     CK(cudaMemcpyAsync(score, ds, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     dfree(dX, st); dfree(ds, st);
+    return SHB_OK;
+}
+
+extern "C" int shb_launch_groove_theta(const long long* off, int n_set, uint32_t max_peaks, const double* peak_theta, const float* proba1,
+                                       float threshold, double* bg, double* dens_max, cudaStream_t st);
+
+SHB_API int shb_groove_theta(int32_t n_set, const int64_t* off, const double* peak_theta, const float* proba1, float threshold,
+                             double* bg_theta, double* density_max) {
+    SHB_ENTER;
+    if (!g.inited) return fail(SHB_E_STATE, "shb_init not called");
+    if (n_set < 0 || !off || !bg_theta || (off[n_set] > 0 && (!peak_theta || !proba1))) return fail(SHB_E_INVALID, "bad argument");
+    if (n_set == 0) return SHB_OK;
+    const int64_t n = off[n_set];
+    int64_t mx = 0;
+    for (int i = 0; i < n_set; ++i) { if (off[i + 1] < off[i]) return fail(SHB_E_INVALID, "offsets decrease"); mx = std::max(mx, off[i + 1] - off[i]); }
+    if ((size_t)mx * 8 > g.smem_optin - 1024) return fail(SHB_E_CAPACITY, "%lld peaks in one set", (long long)mx);
+    cudaStream_t st = g.stream;
+    long long* d_off = nullptr; double *d_th = nullptr, *d_bg = nullptr; float* d_pr = nullptr;
+    CK(dalloc(&d_off, n_set + 1, st)); CK(dalloc(&d_th, n, st)); CK(dalloc(&d_pr, n, st)); CK(dalloc(&d_bg, 2 * (size_t)n_set, st));
+    CK(cudaMemcpyAsync(d_off, off, (n_set + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (n) {
+        CK(cudaMemcpyAsync(d_th, peak_theta, n * sizeof(double), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_pr, proba1, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    g.launches += shb_launch_groove_theta(d_off, n_set, (uint32_t)mx, d_th, d_pr, threshold, d_bg, d_bg + n_set, st);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(bg_theta, d_bg, n_set * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (density_max) CK(cudaMemcpyAsync(density_max, d_bg + n_set, n_set * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    dfree(d_off, st); dfree(d_th, st); dfree(d_pr, st); dfree(d_bg, st);
     return SHB_OK;
 }
 

@@ -28,11 +28,11 @@ __device__ __forceinline__ double shb_warp_sum(double v) {
     return v;
 }
 
-// which sweep an output row belongs to (few sweeps: linear scan)
+// which sweep an output row belongs to: last s with src[s].out_row0 <= row (binary search: a batch lists one sweep per bone)
 __device__ __forceinline__ int shb_find_src(const ShbRowSrc* src, int n_src, uint32_t row) {
-    int s = 0;
-    while (s + 1 < n_src && row >= src[s + 1].out_row0) ++s;
-    return s;
+    int lo = 0, hi = n_src;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (src[mid].out_row0 <= row) lo = mid; else hi = mid; }
+    return lo;
 }
 
 __global__ void __launch_bounds__(128) k_groove_features(const ShbRowSrc* __restrict__ src, int n_src, uint32_t total_rows,
@@ -387,6 +387,47 @@ __global__ void __launch_bounds__(256) k_ray_cast(const double4* __restrict__ ve
     }
 }
 
+// bicipital_groove.py:184-188: the groove angle of a bone = arg-max over np.linspace(-pi, pi, 1024) of the linear-kernel
+// density (bandwidth 1: sum of max(0, 1 - |t - theta_i|)) of the peaks the forest accepted (probability > threshold).
+// One CTA per bone, one thread per grid angle, the accepted peaks staged in shared memory in peak order; arg-max with
+// np.argmax's first-occurrence rule.  (sklearn's KernelDensity returns the log of the same sum over a constant: same arg-max.)
+__global__ void __launch_bounds__(1024) k_groove_theta(const long long* __restrict__ off, const double* __restrict__ peak_theta,
+                                                       const float* __restrict__ proba1, float threshold, double* __restrict__ bg,
+                                                       double* __restrict__ dens_max) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* pts = reinterpret_cast<double*>(smem);
+    __shared__ uint32_t n_acc;
+    __shared__ double red_v[32];
+    __shared__ uint32_t red_i[32];
+    const uint32_t b = blockIdx.x, k = threadIdx.x, lane = k & 31u, w = k >> 5;
+    const long long p0 = off[b], p1 = off[b + 1];
+    if (k == 0) {                                                   // compaction in peak order (a few thousand peaks)
+        uint32_t m = 0;
+        for (long long i = p0; i < p1; ++i) if (proba1[i] > threshold) pts[m++] = peak_theta[i];
+        n_acc = m;
+    }
+    __syncthreads();
+    const double pi = 3.141592653589793;
+    const double step = __ddiv_rn(__dsub_rn(pi, -pi), 1023.0);
+    const double t = k == 1023u ? pi : __dadd_rn(__dmul_rn((double)k, step), -pi);       // np.linspace
+    double dens = 0.0;
+    const uint32_t m = n_acc;
+    for (uint32_t i = 0; i < m; ++i) { const double v = __dsub_rn(1.0, fabs(__dsub_rn(t, pts[i]))); dens = __dadd_rn(dens, v > 0.0 ? v : 0.0); }
+    double bv = dens; uint32_t bi = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[w] = bv; red_i[w] = bi; }
+    __syncthreads();
+    if (k == 0) {
+        for (int q = 1; q < 32; ++q) if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+        bg[b] = bi == 1023u ? pi : __dadd_rn(__dmul_rn((double)bi, step), -pi);
+        if (dens_max) dens_max[b] = bv;
+    }
+}
+
 extern "C" {
 int shb_launch_ray_cast(const double4* vert, const int4* face, int64_t n_face, const double* org, const double* dir, int n_ray, int max_hits,
                         int32_t* hit_ray, int32_t* hit_tri, double* hit_loc, double* hit_dist, uint32_t* n_hits, cudaStream_t st) {
@@ -423,6 +464,14 @@ int shb_launch_forest(const float* X, uint32_t n, uint32_t n_feat, uint32_t n_tr
     if (!n) return 0;
     const size_t tot = (size_t)n * n_trees;
     k_forest<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, n, n_feat, n_trees, root, feature, value, tchild, fchild, weight, score);
+    return 1;
+}
+int shb_launch_groove_theta(const long long* off, int n_set, uint32_t max_peaks, const double* peak_theta, const float* proba1, float threshold,
+                            double* bg, double* dens_max, cudaStream_t st) {
+    if (!n_set) return 0;
+    const size_t smem = 8 * (size_t)(max_peaks ? max_peaks : 1);
+    cudaFuncSetAttribute(k_groove_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_groove_theta<<<n_set, 1024, smem, st>>>(off, peak_theta, proba1, threshold, bg, dens_max);
     return 1;
 }
 }

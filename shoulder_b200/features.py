@@ -33,20 +33,23 @@ def groove_features(result, sweeps, zs_list, canal_axes):
     zs = np.ascontiguousarray(np.concatenate([np.asarray(z, dtype=np.float64) for z in zs_list]))
     axes = np.ascontiguousarray(np.asarray(canal_axes, dtype=np.float64).reshape(len(sweeps), 2, 3))
     rows = len(zs)
-    feat = np.zeros((rows, N_TOP, N_FEAT)); theta = np.zeros((rows, N_TOP))
-    idx = np.zeros((rows, N_TOP), dtype=np.int32); cnt = np.zeros(rows, dtype=np.int32)
+    feat = _lib.pinned_empty((rows, N_TOP, N_FEAT), np.float64); theta = _lib.pinned_empty((rows, N_TOP), np.float64)
+    idx = _lib.pinned_empty((rows, N_TOP), np.int32); cnt = _lib.pinned_empty((rows,), np.int32)
     _lib.check(lib.shb_groove_features(result._h, len(sweeps), _p(sweeps), _p(zs), _p(axes), _p(feat), _p(theta), _p(idx), _p(cnt)))
-    out, r0 = [], 0
+    # one gather for the whole batch, then per-bone slices (the StandardScaler is per bone)
+    sel = np.arange(N_TOP)[None, :] < cnt[:, None]
+    raw_all, theta_all, idx_all = feat[sel], theta[sel], idx[sel]
+    out, r0, p0 = [], 0, 0
     for z in zs_list:
         n = len(z)
-        c = cnt[r0:r0 + n]
-        sel = np.arange(N_TOP)[None, :] < c[:, None]
-        raw = feat[r0:r0 + n][sel]
+        c = cnt[r0:r0 + n].copy()
+        p1 = p0 + int(c.sum())
+        raw = raw_all[p0:p1]
         mean, std = raw.mean(axis=0), raw.std(axis=0)
         std = np.where(std == 0.0, 1.0, std)                         # sklearn's _handle_zeros_in_scale
-        out.append({"raw": raw, "X": (raw - mean) / std, "peak_theta": theta[r0:r0 + n][sel],
-                    "peak_row": np.repeat(np.arange(n), c), "peak_index": idx[r0:r0 + n][sel], "n_peaks": c.copy()})
-        r0 += n
+        out.append({"raw": raw, "X": (raw - mean) / std, "peak_theta": theta_all[p0:p1],
+                    "peak_row": np.repeat(np.arange(n), c), "peak_index": idx_all[p0:p1], "n_peaks": c})
+        r0, p0 = r0 + n, p1
     return out
 
 
@@ -56,6 +59,19 @@ def groove_theta(peak_theta, proba1, threshold: float = 0.4) -> float:
     tlin = np.linspace(-np.pi, np.pi, 1024)
     dens = np.maximum(0.0, 1.0 - np.abs(tlin[:, None] - pts[None, :])).sum(axis=1)
     return float(tlin[np.argmax(dens)])
+
+
+def groove_theta_batch(peak_thetas, probas1, threshold: float = 0.4) -> np.ndarray:
+    """:func:`groove_theta` for many bones in one device call (``shb_groove_theta``): lists of per-bone peak angles and
+    class-1 probabilities -> (n_bones,) groove angles.  Same grid, same first-maximum rule; the density is summed in peak
+    order (numpy sums pairwise), so the two can only differ where two grid angles tie within rounding."""
+    off = np.cumsum([0] + [len(t) for t in peak_thetas]).astype(np.int64)
+    th = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=np.float64) for t in peak_thetas])) if off[-1] else np.zeros(1)
+    pr = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.float32) for q in probas1])) if off[-1] else np.zeros(1, np.float32)
+    bg = np.zeros(len(peak_thetas))
+    _lib.init(_lib._inited if _lib._inited is not None else 0)
+    _lib.check(_lib.load().shb_groove_theta(len(peak_thetas), _p(off), _p(th), _p(pr), C.c_float(threshold), _p(bg), C.c_void_p(0)))
+    return bg
 
 
 def groove_points(result, sweeps, zs_list, bg_thetas, interp_num: int, deg_window: float = 7):
@@ -79,8 +95,8 @@ def neck_image(result, sweeps, bg_thetas, want_shifted: bool = False):
     rows = [hi - lo for lo, hi in wins]
     n = result.array(_lib.ARR_N_SEG, int(sweeps[0])).shape[0]      # noqa: F841  (forces the plane records; N comes from the window array)
     N = result.array_shape(_lib.ARR_ITR_START, int(sweeps[0]))[2]
-    image = np.zeros((sum(rows), N), dtype=np.float32)
-    shft = np.zeros((sum(rows), 2, N)) if want_shifted else None
+    image = _lib.pinned_empty((sum(rows), N), np.float32)
+    shft = _lib.pinned_empty((sum(rows), 2, N), np.float64) if want_shifted else None
     mm = np.zeros((len(sweeps), 2))
     _lib.check(lib.shb_neck_image(result._h, len(sweeps), _p(sweeps), _p(bg), _p(image), _p(shft) if want_shifted else C.c_void_p(0), _p(mm)))
     cuts = np.cumsum([0] + rows)

@@ -110,6 +110,7 @@ def test_gpu_feature_stage_reproduces_the_reference_made_vectors(gpu_backend, na
         kr = np.lexsort((g["peak_theta"], ref["peak_row"]))
         assert np.abs(proba - g["proba"][kr]).max() < 1e-6
         bg = features.groove_theta(ft["peak_theta"][k], proba[:, 1])
+        assert features.groove_theta_batch([ft["peak_theta"][k]], [proba[:, 1]])[0] == bg          # the device arg-max == the host one
     else:
         bg = features.groove_theta(g["peak_theta"], g["proba"][:, 1])
     assert abs(bg - float(g["bg_theta"])) < 1e-12
@@ -122,3 +123,30 @@ def test_gpu_feature_stage_reproduces_the_reference_made_vectors(gpu_backend, na
     assert abs(img.astype(np.float64).sum() - float(g["image_sum"])) < 1e-5 * float(g["image_sum"])
     _, shft_ref, _ = groove.neck_image(orc.itr_start[lo2:hi2], bg)
     assert np.abs(shft - shft_ref).max() < 1e-9 * np.abs(shft_ref).max()
+
+
+@pytest.mark.gpu
+def test_device_groove_angle_equals_the_host_density_arg_max(gpu_backend):
+    """shb_groove_theta against features.groove_theta (numpy, what the reference's KernelDensity arg-max reduces to) on
+    random peak sets of bone-like sizes, several bones per call, incl. an empty set and a set without accepted peaks."""
+    from shoulder_b200 import features
+    rng = np.random.default_rng(3)
+    ths, prs = [], []
+    for n in (2310, 1500, 0, 40, 900):
+        c = rng.uniform(-np.pi, np.pi, 3)                                    # three clusters + background
+        th = np.concatenate([rng.normal(c[k % 3], 0.15, n // 4) for k in range(3)] + [rng.uniform(-np.pi, np.pi, n - 3 * (n // 4))])
+        ths.append(np.clip(th, -np.pi, np.pi)); prs.append(rng.uniform(0, 1, len(th)).astype(np.float32))
+    ths.append(rng.uniform(-3, 3, 50)); prs.append(np.full(50, 0.1, dtype=np.float32))  # nothing accepted: density 0 everywhere -> first grid angle
+    got = features.groove_theta_batch(ths, prs)
+    ref = np.array([features.groove_theta(t, p) for t, p in zip(ths, prs)])
+    # the device sums the density in peak order, numpy pairwise: where two neighbouring grid angles tie within rounding the
+    # arg-max may land on the other one — then the host density at the device's angle must equal the maximum
+    tlin = np.linspace(-np.pi, np.pi, 1024)
+    for g_, r_, th, pr in zip(got, ref, ths, prs):
+        if g_ == r_:
+            continue
+        pts = th[pr > 0.4]
+        dens = np.maximum(0.0, 1.0 - np.abs(tlin[:, None] - pts[None, :])).sum(axis=1)
+        k = int(np.argmin(np.abs(tlin - g_)))
+        assert tlin[k] == g_ and dens[k] >= dens.max() * (1 - 1e-12), (g_, r_)
+    assert (got == ref).sum() >= len(ref) - 1
