@@ -129,15 +129,23 @@ class GpuMesh:
         (``shb_mesh_from_stl``) and the mesh stays resident; ``vertices`` / ``faces`` are read back once for the host-side
         attributes.  ``frame=True`` also applies the oriented frame (``SHB_STL_FRAME``) and returns ``(mesh, info)`` with
         ``info = {transform, z_bounds, z_length, flipped, residuals}``."""
-        from pathlib import Path
-        raw = stl if isinstance(stl, (bytes, bytearray, memoryview)) else Path(stl).read_bytes()
-        buf = np.frombuffer(raw, dtype=np.uint8)
+        import os
         _lib.init(_lib._inited if _lib._inited is not None else 0)
+        # the file goes through page-locked memory (read straight into it when a path is given): the upload then runs at
+        # PCIe speed instead of through the driver's pageable staging
+        if isinstance(stl, (bytes, bytearray, memoryview)):
+            buf = _lib.pinned_empty((len(stl),), np.uint8)
+            buf[:] = np.frombuffer(stl, dtype=np.uint8)
+        else:
+            buf = _lib.pinned_empty((os.path.getsize(stl),), np.uint8)
+            with open(stl, "rb") as fh:
+                if fh.readinto(memoryview(buf)) != len(buf):
+                    raise IOError(f"short read of {stl}")
         h, nv, nf = C.c_void_p(), C.c_int64(), C.c_int64()
         fo = np.zeros(22)
         _lib.check(_lib.load().shb_mesh_from_stl(_p(buf), len(buf), _lib.STL_FRAME if frame else 0, C.byref(h), C.byref(nv), C.byref(nf), _p(fo)))
         handle = _MeshHandle(adopt=h)
-        v, f = np.empty((nv.value, 3)), np.empty((nf.value, 3), dtype=np.int64)
+        v, f = _lib.pinned_empty((nv.value, 3), np.float64), _lib.pinned_empty((nf.value, 3), np.int64)
         _lib.check(_lib.load().shb_mesh_read(h, _p(v), _p(f)))
         m = cls(v, f)
         m._handle = handle
