@@ -97,3 +97,24 @@ def test_dense_sweep_with_several_contour_planes(gpu_backend, bone_obbs):
     rep = compare_sweep(m.vertices, m.faces, zs, 128, n_angles=90, expect_all_closed=False)
     assert rep["contours"] > len(zs) + 20 and rep["pts_bitexact"] and not rep["h4_exceptions"]
     assert rep["max_rel"] < 1e-12
+
+
+def test_polar_forms_against_numpy_bits(gpu_backend, bone_obbs):
+    """The unroll's polar pass (``shb_polar``: one reciprocal square root per sample feeds both r and theta) against numpy
+    on the samples the device itself delivered: r is ``np.sqrt(x**2 + y**2)`` (slice.py:100-101,138-139) BIT FOR BIT,
+    theta is within 4 ulp of ``np.arctan2`` (slice.py:99,137), and the roll puts the smallest theta first."""
+    from shoulder_b200 import _lib
+    from helpers import run_gpu
+    m = bone_obbs("humerus_right").mesh
+    zs = np.linspace(0.99 * m.vertices[:, 2].max(), 0.99 * m.vertices[:, 2].min(), 700)
+    res = run_gpu(m.vertices, m.faces, zs, 360, _lib.OUT_PLANE | _lib.OUT_ALL_PROFILES)
+    for xy_name, tr_name in ((_lib.ARR_IXY, _lib.ARR_ITR_START), (_lib.ARR_IXY_CENTERED, _lib.ARR_ITR_CENTERED_START)):
+        xy, tr = res.array(xy_name, 0), res.array(tr_name, 0)
+        x, y = xy[:, 0, :], xy[:, 1, :]
+        theta, r = np.arctan2(y, x), np.sqrt(x ** 2 + y ** 2)
+        km = np.argmin(theta, axis=1)
+        idx = (np.arange(x.shape[1])[None, :] + km[:, None]) % x.shape[1]
+        theta, r = np.take_along_axis(theta, idx, 1), np.take_along_axis(r, idx, 1)
+        assert np.array_equal(tr[:, 1, :], r)
+        assert np.abs(tr[:, 0, :] - theta).max() <= 4 * np.spacing(np.pi)
+        assert (tr[:, 0, 0] <= tr[:, 0, :].min(axis=1)).all()
