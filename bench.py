@@ -596,9 +596,9 @@ def landmark_record(gpu: Gpu, bones: int, steps: int):
     """BASELINE configs[4] as far as the checkout allows: the front end of the landmark pipeline on a batch, host buffers
     in, landmark-model inputs out.  Per step: the three default sweeps of every bone with the consumers' windows
     (shb_batch_run_req; the polar stacks stay in HBM), plane records to the host, canal axis per bone from the Full
-    sweep's centroids (canal.py:40-85: a line fit, host numpy), then on the device the groove feature rows
-    (bicipital_groove.py:94-156), the random forest rfc_bg3 (:174-181), on the host the density arg-max (:184-188), and on
-    the device the groove points (:190-238) and the 512-wide float32 neck image (anatomic_neck.py:38-58) the UNet would read
+    sweep's centroids (canal.py:40-85: a line fit, on the device), then the groove feature rows
+    (bicipital_groove.py:94-156), the StandardScaler (:171-172), the random forest rfc_bg3 (:174-181), the density arg-max
+    (:184-188), the groove points (:190-238) and the 512-wide float32 neck image (anatomic_neck.py:38-58) the UNet would read
     (the UNet blobs themselves are not in the checkout)."""
     from shoulder_b200 import _lib, features
     fx = ROOT / "tests" / "golden" / "forest_rfc_bg3.npz"
@@ -618,27 +618,23 @@ def landmark_record(gpu: Gpu, bones: int, steps: int):
     c_lo, c_hi = int((1 - 0.75) * 200), int((1 - 0.35) * 200)
     half = np.array([0.55 * (abs(z[0]) + abs(z[-1])) / 2 for z in z_full])
 
+    fe = features.LandmarkFrontEnd(forest, 512)
+    canal_z = np.stack([z[c_lo:c_hi] for z in z_full])
+
     def step(count=False):
         res = _lib.sweep_batch(None, None, _lib.OUT_PLANE, 0, packed=packed, lazy=True, requests=req)
-        # canal.py:40-85 for every bone at once: centroids((0.35, 0.75)) of the Full sweep + z -> best-fit line (mean + first
-        # right singular vector, what scikit-spatial's Line.best_fit computes)
-        cz = np.stack([np.c_[res.array(_lib.ARR_CENTROID, s)[c_lo:c_hi], z_full[b][c_lo:c_hi]] for b, s in enumerate(full)])
-        mid = cz.mean(axis=1, keepdims=True)
-        dirn = np.linalg.svd(cz - mid)[2][:, 0, :]
-        dirn = np.where(dirn[:, -1:] < 0, -dirn, dirn)
-        axes = np.stack([mid[:, 0] + dirn * half[:, None], mid[:, 0] - dirn * half[:, None]], axis=1)
-        ft = features.groove_features(res, prox, zs_g, axes)
-        cuts = np.cumsum([0] + [len(f["X"]) for f in ft])
-        proba = forest.predict_proba(np.vstack([f["X"] for f in ft]))           # one forest launch for the whole batch
-        bg = features.groove_theta_batch([f["peak_theta"] for f in ft], [proba[a:b, 1] for a, b in zip(cuts[:-1], cuts[1:])])
-        pts = features.groove_points(res, prox, zs_g, bg, 512)
-        imgs = features.neck_image(res, prox, bg)
+        # ONE enqueue, one host wait (shb_landmark_front): canal axes from the plane records on the device (canal.py:40-85),
+        # groove features, StandardScaler, forest, density arg-max, groove points, neck image; then the plane records
+        out = fe(res, full, prox, (c_lo, c_hi), canal_z, half, zs_g)
+        res.fetch(_lib.OUT_PLANE)
         out_bytes = 0
         if count:
-            out_bytes = sum(i[0].nbytes for i in imgs) + sum(p[0].nbytes + p[1].nbytes for p in pts) + sum(f["raw"].nbytes + f["peak_theta"].nbytes for f in ft)
+            out_bytes = sum(out[k].nbytes for k in ("canal_axes", "feat", "peak_theta", "peak_index", "n_peaks", "proba1", "bg_theta", "points",
+                                                    "local_theta", "image", "minmax"))
             out_bytes += 76 * sum(len(sw[2]) for sw in sweeps)                   # plane records
+        chk = float(np.mean(out["bg_theta"]))
         res.close()
-        return out_bytes, float(np.mean(bg))
+        return out_bytes, chk
 
     for _ in range(2):
         d2h, chk = step(True)
@@ -653,6 +649,7 @@ def landmark_record(gpu: Gpu, bones: int, steps: int):
             "h2d_bytes_per_step": int(sum(a.nbytes for a in packed)), "d2h_bytes_per_bone": d2h / bones,
             "delivers": "per bone: plane records of the three sweeps, canal axis, groove feature rows (<= 330 x 7 x 9) + forest probabilities, "
                         "groove angle, 330 groove points, the 512 x 512 float32 neck image",
+            "call": "shoulder_b200._lib.sweep_batch(lazy, per-sweep requests) + shoulder_b200.features.LandmarkFrontEnd (shb_landmark_front: one enqueue, one host wait)",
             "note": "host buffers in, landmark-model inputs out; the polar stacks (4.2 + 2.7 MB per bone) never cross PCIe; mean groove angle %.6f" % chk}
 
 

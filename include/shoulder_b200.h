@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SHB_ABI_VERSION 3
+#define SHB_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define SHB_API __attribute__((visibility("default")))
@@ -299,6 +299,43 @@ SHB_API int shb_forest_free(shb_forest* forest);
  * bg_theta [n_set] receives the arg-max angle (first maximum, like np.argmax), density_max [n_set] (may be NULL) its value. */
 SHB_API int shb_groove_theta(int32_t n_set, const int64_t* off, const double* peak_theta, const float* proba1, float threshold,
                              double* bg_theta, double* density_max);
+
+/* The landmark front end of a batch in ONE enqueue and ONE host wait (BASELINE configs[4]): what bone.Humerus runs between
+ * slice.py's arrays and its landmark models, for n_bones bones whose sweeps are resident in `result`:
+ *   canal axis        canal.py:40-85 (centroids((0.35, 0.75)) of the Full sweep + z -> Line.best_fit, pointed proximally,
+ *                     end points at +- half along it) from the plane records on the device;
+ *   groove features   as shb_groove_features, the canal axis taken from the step above;
+ *   StandardScaler    bicipital_groove.py:171-172, per bone over all its peaks (numpy's summation order) -> float32 X;
+ *   forest            as shb_forest_predict, over the slot layout [rows][7] (slots >= n_peaks[row] are skipped);
+ *   groove angle      as shb_groove_theta; groove points as shb_groove_points; neck image as shb_neck_image.
+ * The polar stacks never leave the device; every output pointer may be NULL (not copied).  Peaks keep the slot layout of
+ * shb_groove_features: row-major order over (row, slot < n_peaks[row]) is the order of the reference's per-row appends. */
+typedef struct shb_landmark_args {
+    int32_t n_bones;
+    int32_t canal_lo, canal_hi;       /* rows of the Full sweep used by the canal fit: Slices._cutoff((0.35, 0.75)) */
+    const int32_t* full_sweeps;       /* [n_bones] sweep whose plane records feed the canal fit */
+    const int32_t* prox_sweeps;       /* [n_bones] sweep holding the itr_start / itr_centered_start windows */
+    const double* canal_z;            /* [n_bones][canal_hi - canal_lo] z of those rows (OBB frame) */
+    const double* canal_half;         /* [n_bones] obb.z_length * mean(cutoff_pcts) / 2 (canal.py:73-75) */
+    const double* groove_zs;          /* z of every row of the itr_centered_start windows, bones concatenated */
+    shb_forest* forest;
+    float threshold;                  /* bicipital_groove.py:183: 0.4 */
+    int32_t ivar;                     /* half window of the local-minimum search, in samples (bicipital_groove.py:196) */
+    double* canal_axes;               /* [n_bones][2][3] */
+    double* feat;                     /* [rows][7][9] */
+    double* peak_theta;               /* [rows][7] */
+    int32_t* peak_index;              /* [rows][7] */
+    int32_t* n_peaks;                 /* [rows] */
+    float* X;                         /* [rows][7][9] scaled features (0 in unused slots) */
+    float* proba1;                    /* [rows][7] class-1 score */
+    double* scaler;                   /* [n_bones][2][9] mean_, scale_ */
+    double* bg_theta;                 /* [n_bones] */
+    double* points;                   /* [rows][3] */
+    double* local_theta;              /* [rows] */
+    float* image;                     /* [image rows][N] */
+    double* minmax;                   /* [n_bones][2] */
+} shb_landmark_args;
+SHB_API int shb_landmark_front(shb_result* result, const shb_landmark_args* args);
 
 SHB_API const char* shb_last_error(void);
 SHB_API int shb_abi_version(void);

@@ -14,7 +14,7 @@ import os as _os
 LIB_PATH = Path(_os.environ.get("SHB_LIB") or Path(__file__).resolve().parent / "libshoulder_b200.so")      # SHB_LIB: experiments only
 
 # --- constants mirrored from include/shoulder_b200.h ---------------------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 OUT_PLANE, OUT_SEGMENTS, OUT_CONTOURS = 0x001, 0x002, 0x004
 OUT_IXY, OUT_IXY_CENTERED, OUT_ITR, OUT_ITR_START = 0x008, 0x010, 0x020, 0x040
 OUT_ITR_CENTERED, OUT_ITR_CENTERED_START, OUT_RADIAL = 0x080, 0x100, 0x200
@@ -38,7 +38,7 @@ EXPORTS = (
     "shb_profile_read", "shb_trim", "shb_launch_count", "shb_last_error", "shb_abi_version",
     "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section", "shb_ray_cast",
     "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
-    "shb_mesh_from_stl", "shb_mesh_read", "shb_groove_theta", "shb_host_alloc", "shb_host_free",
+    "shb_mesh_from_stl", "shb_mesh_read", "shb_groove_theta", "shb_host_alloc", "shb_host_free", "shb_landmark_front",
 )
 
 
@@ -87,6 +87,7 @@ def load() -> C.CDLL:
     lib.shb_forest_create.argtypes = [i32, i32, i32, p, p, p, p, p, p, pp]
     lib.shb_forest_predict.argtypes = [p, p, i32, p]
     lib.shb_forest_free.argtypes = [p]
+    lib.shb_landmark_front.argtypes = [p, p]
     lib.shb_profile_enable.argtypes = [C.c_int]
     lib.shb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
     lib.shb_launch_count.restype = i64

@@ -1229,6 +1229,14 @@ int shb_launch_neck_image(const ShbRowSrc* src, int n_src, uint32_t rows, uint32
                           unsigned long long* mm, float* image, double* mm_out, cudaStream_t st);
 int shb_launch_forest(const float* X, uint32_t n, uint32_t n_feat, uint32_t n_trees, const uint32_t* root, const int32_t* feature,
                       const float* value, const uint32_t* tchild, const uint32_t* fchild, const float* weight, float* score, cudaStream_t st);
+int shb_launch_canal_axes(const ShbCanalJob* jobs, int n_jobs, const double* centroid, const double* z, ShbRowSrc* src, double* axes, cudaStream_t st);
+int shb_launch_groove_scale(const ShbRowSrc* src, int n_src, uint32_t max_rows, size_t smem_limit, const double* feat, const int32_t* cnt, float* X,
+                            double* stats, cudaStream_t st);
+int shb_launch_forest_slots(const float* X, const int32_t* cnt, uint32_t n_rows, uint32_t n_feat, uint32_t n_trees, const uint32_t* root,
+                            const int32_t* feature, const float* value, const uint32_t* tchild, const uint32_t* fchild, const float* weight,
+                            float* score, cudaStream_t st);
+int shb_launch_groove_theta_slots(const ShbRowSrc* src, int n_src, uint32_t max_rows, const double* theta, const int32_t* cnt, const float* score,
+                                  float threshold, double* bg, double* dens_max, cudaStream_t st);
 }
 
 namespace {
@@ -1460,6 +1468,85 @@ SHB_API int shb_groove_theta(int32_t n_set, const int64_t* off, const double* pe
     if (density_max) CK(cudaMemcpyAsync(density_max, d_bg + n_set, n_set * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     dfree(d_off, st); dfree(d_th, st); dfree(d_pr, st); dfree(d_bg, st);
+    return SHB_OK;
+}
+
+SHB_API int shb_landmark_front(shb_result* r, const shb_landmark_args* a) {
+    SHB_ENTER;
+    if (!r || !a || a->n_bones <= 0 || !a->full_sweeps || !a->prox_sweeps || !a->canal_z || !a->canal_half || !a->groove_zs || !a->forest ||
+        a->canal_hi <= a->canal_lo || a->canal_lo < 0 || a->ivar < 1)
+        return fail(SHB_E_INVALID, "bad argument");
+    const int nb = a->n_bones;
+    const shb_forest* f = a->forest;
+    if (f->n_feat != 9) return fail(SHB_E_INVALID, "the groove forest must read 9 features, this one reads %u", f->n_feat);
+    std::vector<ShbRowSrc> gsrc, isrc; uint32_t gN = 0, iN = 0;
+    const int64_t grows = row_sources(r, 5, nb, a->prox_sweeps, a->groove_zs, nullptr, gsrc, gN);
+    if (grows < 0) return (int)grows;
+    const int64_t irows = row_sources(r, 3, nb, a->prox_sweeps, nullptr, nullptr, isrc, iN);
+    if (irows < 0) return (int)irows;
+    if (gN > 1024) return fail(SHB_E_CAPACITY, "interp_num %u > 1024", gN);
+    for (auto& q : isrc) if (q.N != iN || q.N < 3 || q.N > 1024) return fail(SHB_E_INVALID, "the sweeps of one image call must share interp_num (3..1024)");
+    const uint32_t crow = (uint32_t)(a->canal_hi - a->canal_lo);
+    std::vector<ShbCanalJob> jobs(nb);
+    uint32_t max_rows = 0;
+    for (int k = 0; k < nb; ++k) {
+        const int s = a->full_sweeps[k];
+        if (s < 0 || s >= (int)r->sweeps.size()) return fail(SHB_E_INVALID, "sweep %d out of range", s);
+        const ShbSweep& sw = r->sweeps[s];
+        if ((uint32_t)a->canal_hi > sw.n_plane) return fail(SHB_E_INVALID, "canal rows %d..%d of a sweep of %u planes", a->canal_lo, a->canal_hi, sw.n_plane);
+        jobs[k] = {sw.plane_off + (uint32_t)a->canal_lo, crow, (uint32_t)k * crow, 0u, a->canal_half[k]};
+        max_rows = std::max(max_rows, gsrc[k].rows);
+    }
+    if ((size_t)max_rows * 7 * 8 + 1024 > g.smem_optin) return fail(SHB_E_CAPACITY, "%u rows in one groove window", max_rows);
+    cudaStream_t st = r->stream ? r->stream : g.stream;
+    if (r->done) CK(cudaStreamWaitEvent(st, r->done, 0));
+    const size_t G = (size_t)grows, tot = (size_t)irows * iN;
+    // one block of device memory, carved
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_gsrc = carve(nb * sizeof(ShbRowSrc)), o_isrc = carve(nb * sizeof(ShbRowSrc)), o_jobs = carve(nb * sizeof(ShbCanalJob)),
+                 o_cz = carve((size_t)nb * crow * 8), o_zs = carve(G * 8), o_axes = carve((size_t)nb * 48), o_feat = carve(G * 63 * 8),
+                 o_th = carve(G * 7 * 8), o_idx = carve(G * 7 * 4), o_cnt = carve(G * 4), o_X = carve(G * 63 * 4), o_score = carve(G * 7 * 4),
+                 o_stats = carve((size_t)nb * 18 * 8), o_bg = carve((size_t)nb * 16), o_pts = carve(G * 24), o_lt = carve(G * 8),
+                 o_vals = carve(tot * 8), o_mm = carve((size_t)nb * 16), o_mmo = carve((size_t)nb * 16), o_img = carve(tot * 4);
+    unsigned char* D = nullptr;
+    CK(dalloc_bytes(reinterpret_cast<void**>(&D), off, st));
+    // small inputs: one pinned staging block, one copy each (they are a few KB)
+    Staging stg;
+    CK(stg.copy(D + o_gsrc, gsrc.data(), nb * sizeof(ShbRowSrc), st)); CK(stg.copy(D + o_isrc, isrc.data(), nb * sizeof(ShbRowSrc), st));
+    CK(stg.copy(D + o_jobs, jobs.data(), nb * sizeof(ShbCanalJob), st)); CK(stg.copy(D + o_cz, a->canal_z, (size_t)nb * crow * 8, st));
+    CK(stg.copy(D + o_zs, a->groove_zs, G * 8, st));
+    std::vector<unsigned long long> mm0(2 * (size_t)nb);
+    for (int k = 0; k < nb; ++k) { mm0[2 * k] = ~0ull; mm0[2 * k + 1] = 0ull; }
+    CK(stg.copy(D + o_mm, mm0.data(), mm0.size() * 8, st));
+    CK(cudaMemsetAsync(D + o_feat, 0, o_idx - o_feat, st));                      // feat, theta
+    CK(cudaMemsetAsync(D + o_idx, 0xFF, G * 7 * 4, st));
+    CK(cudaMemsetAsync(D + o_score, 0, G * 7 * 4, st));
+    ShbRowSrc* d_gsrc = reinterpret_cast<ShbRowSrc*>(D + o_gsrc); ShbRowSrc* d_isrc = reinterpret_cast<ShbRowSrc*>(D + o_isrc);
+    double* d_bg = reinterpret_cast<double*>(D + o_bg);
+    g.launches += shb_launch_canal_axes(reinterpret_cast<ShbCanalJob*>(D + o_jobs), nb, r->d.o_centroid, reinterpret_cast<double*>(D + o_cz), d_gsrc,
+                                        reinterpret_cast<double*>(D + o_axes), st);
+    g.launches += shb_launch_groove_features(d_gsrc, nb, (uint32_t)G, gN, reinterpret_cast<double*>(D + o_zs), reinterpret_cast<double*>(D + o_feat),
+                                             reinterpret_cast<double*>(D + o_th), reinterpret_cast<int32_t*>(D + o_idx), reinterpret_cast<int32_t*>(D + o_cnt), st);
+    g.launches += shb_launch_groove_scale(d_gsrc, nb, max_rows, g.smem_optin, reinterpret_cast<double*>(D + o_feat), reinterpret_cast<int32_t*>(D + o_cnt),
+                                          reinterpret_cast<float*>(D + o_X), reinterpret_cast<double*>(D + o_stats), st);
+    g.launches += shb_launch_forest_slots(reinterpret_cast<float*>(D + o_X), reinterpret_cast<int32_t*>(D + o_cnt), (uint32_t)G, f->n_feat, f->n_trees, f->root,
+                                          f->feature, f->value, f->tchild, f->fchild, f->weight, reinterpret_cast<float*>(D + o_score), st);
+    g.launches += shb_launch_groove_theta_slots(d_gsrc, nb, max_rows, reinterpret_cast<double*>(D + o_th), reinterpret_cast<int32_t*>(D + o_cnt),
+                                                reinterpret_cast<float*>(D + o_score), a->threshold, d_bg, d_bg + nb, st);
+    g.launches += shb_launch_groove_points(d_gsrc, nb, (uint32_t)G, reinterpret_cast<double*>(D + o_zs), d_bg, a->ivar, r->d.o_centroid,
+                                           reinterpret_cast<double*>(D + o_pts), reinterpret_cast<double*>(D + o_lt), st);
+    g.launches += shb_launch_neck_image(d_isrc, nb, (uint32_t)irows, iN, d_bg, reinterpret_cast<double*>(D + o_vals), nullptr,
+                                        reinterpret_cast<unsigned long long*>(D + o_mm), reinterpret_cast<float*>(D + o_img), reinterpret_cast<double*>(D + o_mmo), st);
+    CK(cudaGetLastError());
+    auto back = [&](void* dst, size_t o, size_t bytes) -> cudaError_t { return dst && bytes ? cudaMemcpyAsync(dst, D + o, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+    CK(back(a->canal_axes, o_axes, (size_t)nb * 48)); CK(back(a->feat, o_feat, G * 63 * 8)); CK(back(a->peak_theta, o_th, G * 7 * 8));
+    CK(back(a->peak_index, o_idx, G * 7 * 4)); CK(back(a->n_peaks, o_cnt, G * 4)); CK(back(a->X, o_X, G * 63 * 4)); CK(back(a->proba1, o_score, G * 7 * 4));
+    CK(back(a->scaler, o_stats, (size_t)nb * 18 * 8)); CK(back(a->bg_theta, o_bg, (size_t)nb * 8)); CK(back(a->points, o_pts, G * 24));
+    CK(back(a->local_theta, o_lt, G * 8)); CK(back(a->image, o_img, tot * 4)); CK(back(a->minmax, o_mmo, (size_t)nb * 16));
+    CK(cudaStreamSynchronize(st));
+    stg.release();
+    dfree(D, st);
     return SHB_OK;
 }
 

@@ -428,6 +428,171 @@ __global__ void __launch_bounds__(1024) k_groove_theta(const long long* __restri
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The landmark front end in ONE enqueue (shb_landmark_front): what the step-by-step calls above leave to the host between
+// them, on the device, so that a batch of bones goes from resident polar stacks to landmark-model inputs with one
+// host wait: canal axis (canal.py:40-85), StandardScaler (bicipital_groove.py:171-172), forest and density arg-max over
+// the slot layout (rows, 7) the feature kernel writes — no compaction, the peaks are visited in row-major slot order, which
+// IS the order of the reference's per-row appends.
+// ------------------------------------------------------------------------------------------
+
+// canal.py:40-85 + scikit-spatial Line.best_fit: centroid = points.mean(axis=0) (numpy adds the rows in order), direction =
+// first right singular vector of the centred points = eigenvector of the largest eigenvalue of their 3x3 scatter matrix
+// (cyclic Jacobi), pointed proximally (direction[-1] >= 0), axis = centroid +- direction * half.  One warp per bone.
+__global__ void __launch_bounds__(32) k_canal_axes(const ShbCanalJob* __restrict__ jobs, int n_jobs, const double* __restrict__ centroid /*[plane][2]*/,
+                                                   const double* __restrict__ z, ShbRowSrc* __restrict__ src /*cu[] written*/,
+                                                   double* __restrict__ axes /*[n][2][3]*/) {
+    const int b = blockIdx.x;
+    if (b >= n_jobs) return;
+    const ShbCanalJob J = jobs[b];
+    const uint32_t lane = threadIdx.x, n = J.rows;
+    const double* c = centroid + 2 * (size_t)J.plane0;
+    const double* zz = z + J.z_off;
+    double mean = 0.0;
+    if (lane < 3) {
+        double acc = 0.0;
+        for (uint32_t i = 0; i < n; ++i) acc = __dadd_rn(acc, lane < 2 ? c[2 * (size_t)i + lane] : zz[i]);
+        mean = __ddiv_rn(acc, (double)n);
+    }
+    const double mx = __shfl_sync(0xffffffffu, mean, 0), my = __shfl_sync(0xffffffffu, mean, 1), mz = __shfl_sync(0xffffffffu, mean, 2);
+    double sxx = 0, sxy = 0, sxz = 0, syy = 0, syz = 0, szz = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const double dx = c[2 * (size_t)i] - mx, dy = c[2 * (size_t)i + 1] - my, dz = zz[i] - mz;
+        sxx += dx * dx; sxy += dx * dy; sxz += dx * dz; syy += dy * dy; syz += dy * dz; szz += dz * dz;
+    }
+    sxx = shb_warp_sum(sxx); sxy = shb_warp_sum(sxy); sxz = shb_warp_sum(sxz); syy = shb_warp_sum(syy); syz = shb_warp_sum(syz); szz = shb_warp_sum(szz);
+    if (lane != 0) return;
+    double a[3][3] = {{sxx, sxy, sxz}, {sxy, syy, syz}, {sxz, syz, szz}}, v[3][3];
+    shb_jacobi3(a, v);
+    int m = 0;
+    if (a[1][1] > a[m][m]) m = 1;
+    if (a[2][2] > a[m][m]) m = 2;
+    double d[3] = {v[0][m], v[1][m], v[2][m]};
+    const double nrm = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const double sg = d[2] < 0.0 ? -1.0 : 1.0;
+    for (int k = 0; k < 3; ++k) d[k] = sg * d[k] / nrm;
+    const double mid[3] = {mx, my, mz};
+    double ax[6];
+    for (int k = 0; k < 3; ++k) { ax[k] = mid[k] + d[k] * J.half_len; ax[3 + k] = mid[k] - d[k] * J.half_len; }
+    for (int k = 0; k < 6; ++k) axes[6 * (size_t)b + k] = ax[k];
+    // utils.unit_vector(axis[0], axis[1]) as the host path computes it for the feature kernel (row_sources)
+    const double vx = ax[0] - ax[3], vy = ax[1] - ax[4], vz = ax[2] - ax[5];
+    const double vn = sqrt(vx * vx + vy * vy + vz * vz);
+    src[b].cu[0] = vx / vn; src[b].cu[1] = vy / vn; src[b].cu[2] = vz / vn;
+}
+
+// sklearn StandardScaler over all peaks of one bone: mean_ = X.mean(axis=0), scale_ = X.std(axis=0) with zeros -> 1, X' = (X - mean_)
+// / scale_, cast to float32 for the forest.  numpy reduces a C-ordered (n, 9) array over axis 0 by adding the rows in order,
+// so one thread per column adding in row-major slot order reproduces both statistics bit for bit.  One CTA per bone; the bone's
+// feature rows are staged in shared memory when they fit (330 rows x 504 B).
+template <bool STAGED>
+__global__ void __launch_bounds__(256) k_groove_scale(const ShbRowSrc* __restrict__ src, const double* __restrict__ feat,
+                                                      const int32_t* __restrict__ cnt, float* __restrict__ X /*[rows][7][9]*/,
+                                                      double* __restrict__ stats /*[n_src][2][9] or null*/) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ double s_mean[SHB_F_NFEAT], s_std[SHB_F_NFEAT];
+    const ShbRowSrc S = src[blockIdx.x];
+    const uint32_t rows = S.rows, tid = threadIdx.x;
+    constexpr uint32_t RW = SHB_F_TOP * SHB_F_NFEAT;
+    const double* g = feat + (size_t)S.out_row0 * RW;
+    const int32_t* c = cnt + S.out_row0;
+    const double* f = g;
+    if (STAGED) {
+        double* sf = reinterpret_cast<double*>(smem);
+        for (uint32_t i = tid; i < rows * RW; i += 256) sf[i] = g[i];
+        f = sf;
+    }
+    __syncthreads();
+    if (tid < SHB_F_NFEAT) {
+        double acc = 0.0; uint32_t n = 0;
+        for (uint32_t r = 0; r < rows; ++r) {
+            const uint32_t k = (uint32_t)c[r];
+            for (uint32_t q = 0; q < k; ++q) acc = __dadd_rn(acc, f[r * RW + q * SHB_F_NFEAT + tid]);
+            n += k;
+        }
+        const double mean = __ddiv_rn(acc, (double)n);
+        acc = 0.0;
+        for (uint32_t r = 0; r < rows; ++r) {
+            const uint32_t k = (uint32_t)c[r];
+            for (uint32_t q = 0; q < k; ++q) { const double dlt = __dsub_rn(f[r * RW + q * SHB_F_NFEAT + tid], mean); acc = __dadd_rn(acc, __dmul_rn(dlt, dlt)); }
+        }
+        double sd = __dsqrt_rn(__ddiv_rn(acc, (double)n));
+        if (sd == 0.0) sd = 1.0;                                      // sklearn _handle_zeros_in_scale
+        s_mean[tid] = mean; s_std[tid] = sd;
+        if (stats) { stats[(size_t)blockIdx.x * 2 * SHB_F_NFEAT + tid] = mean; stats[(size_t)blockIdx.x * 2 * SHB_F_NFEAT + SHB_F_NFEAT + tid] = sd; }
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < rows * RW; i += 256) {
+        const uint32_t r = i / RW, q = (i % RW) / SHB_F_NFEAT, j = i % SHB_F_NFEAT;
+        X[(size_t)S.out_row0 * RW + i] = q < (uint32_t)c[r] ? (float)__ddiv_rn(__dsub_rn(f[i], s_mean[j]), s_std[j]) : 0.f;
+    }
+}
+
+// k_forest over the slot layout: sample = row * 7 + slot, slots at or beyond the row's peak count are skipped
+__global__ void __launch_bounds__(256) k_forest_slots(const float* __restrict__ X, const int32_t* __restrict__ cnt, uint32_t n_rows, uint32_t n_feat,
+                                                      uint32_t n_trees, const uint32_t* __restrict__ root, const int32_t* __restrict__ feature,
+                                                      const float* __restrict__ value, const uint32_t* __restrict__ tchild,
+                                                      const uint32_t* __restrict__ fchild, const float* __restrict__ weight,
+                                                      float* __restrict__ score /*[n_rows * 7], zeroed*/) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (size_t)n_rows * SHB_F_TOP * n_trees) return;
+    const uint32_t s = (uint32_t)(i / n_trees), t = (uint32_t)(i % n_trees);
+    if ((int32_t)(s % SHB_F_TOP) >= cnt[s / SHB_F_TOP]) return;
+    uint32_t cur = root[t];
+    while (feature[cur] >= 0) cur = X[(size_t)s * n_feat + feature[cur]] <= value[cur] ? tchild[cur] : fchild[cur];
+    atomicAdd(score + s, weight[cur]);
+}
+
+// k_groove_theta over the slot layout: one CTA per bone; warp 0 compacts the accepted peaks in row-major slot order
+__global__ void __launch_bounds__(1024) k_groove_theta_slots(const ShbRowSrc* __restrict__ src, const double* __restrict__ theta /*[rows][7]*/,
+                                                             const int32_t* __restrict__ cnt, const float* __restrict__ score, float threshold,
+                                                             double* __restrict__ bg, double* __restrict__ dens_max) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* pts = reinterpret_cast<double*>(smem);
+    __shared__ uint32_t n_acc;
+    __shared__ double red_v[32];
+    __shared__ uint32_t red_i[32];
+    const uint32_t b = blockIdx.x, k = threadIdx.x, lane = k & 31u, w = k >> 5;
+    const ShbRowSrc S = src[b];
+    if (w == 0) {
+        uint32_t m = 0;
+        const uint32_t tot = S.rows * SHB_F_TOP;
+        for (uint32_t e0 = 0; e0 < tot; e0 += 32) {
+            const uint32_t e = e0 + lane;
+            bool ok = false; double t = 0.0;
+            if (e < tot) {
+                const uint32_t row = S.out_row0 + e / SHB_F_TOP, slot = e % SHB_F_TOP;
+                if ((int32_t)slot < cnt[row] && score[(size_t)row * SHB_F_TOP + slot] > threshold) { ok = true; t = theta[(size_t)row * SHB_F_TOP + slot]; }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) pts[m + __popc(bal & ((1u << lane) - 1u))] = t;
+            m += __popc(bal);
+        }
+        if (lane == 0) n_acc = m;
+    }
+    __syncthreads();
+    const double pi = 3.141592653589793;
+    const double step = __ddiv_rn(__dsub_rn(pi, -pi), 1023.0);
+    const double t = k == 1023u ? pi : __dadd_rn(__dmul_rn((double)k, step), -pi);       // np.linspace
+    double dens = 0.0;
+    const uint32_t m = n_acc;
+    for (uint32_t i = 0; i < m; ++i) { const double v = __dsub_rn(1.0, fabs(__dsub_rn(t, pts[i]))); dens = __dadd_rn(dens, v > 0.0 ? v : 0.0); }
+    double bv = dens; uint32_t bi = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o); const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[w] = bv; red_i[w] = bi; }
+    __syncthreads();
+    if (k == 0) {
+        for (int q = 1; q < 32; ++q) if (red_v[q] > bv || (red_v[q] == bv && red_i[q] < bi)) { bv = red_v[q]; bi = red_i[q]; }
+        bg[b] = bi == 1023u ? pi : __dadd_rn(__dmul_rn((double)bi, step), -pi);
+        if (dens_max) dens_max[b] = bv;
+    }
+}
+
 extern "C" {
 int shb_launch_ray_cast(const double4* vert, const int4* face, int64_t n_face, const double* org, const double* dir, int n_ray, int max_hits,
                         int32_t* hit_ray, int32_t* hit_tri, double* hit_loc, double* hit_dist, uint32_t* n_hits, cudaStream_t st) {
@@ -472,6 +637,39 @@ int shb_launch_groove_theta(const long long* off, int n_set, uint32_t max_peaks,
     const size_t smem = 8 * (size_t)(max_peaks ? max_peaks : 1);
     cudaFuncSetAttribute(k_groove_theta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_groove_theta<<<n_set, 1024, smem, st>>>(off, peak_theta, proba1, threshold, bg, dens_max);
+    return 1;
+}
+int shb_launch_canal_axes(const ShbCanalJob* jobs, int n_jobs, const double* centroid, const double* z, ShbRowSrc* src, double* axes, cudaStream_t st) {
+    if (n_jobs <= 0) return 0;
+    k_canal_axes<<<n_jobs, 32, 0, st>>>(jobs, n_jobs, centroid, z, src, axes);
+    return 1;
+}
+int shb_launch_groove_scale(const ShbRowSrc* src, int n_src, uint32_t max_rows, size_t smem_limit, const double* feat, const int32_t* cnt, float* X,
+                            double* stats, cudaStream_t st) {
+    if (n_src <= 0) return 0;
+    const size_t need = (size_t)max_rows * SHB_F_TOP * SHB_F_NFEAT * sizeof(double);
+    if (need + 1024 <= smem_limit) {
+        cudaFuncSetAttribute(k_groove_scale<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+        k_groove_scale<true><<<n_src, 256, need, st>>>(src, feat, cnt, X, stats);
+    } else {
+        k_groove_scale<false><<<n_src, 256, 0, st>>>(src, feat, cnt, X, stats);
+    }
+    return 1;
+}
+int shb_launch_forest_slots(const float* X, const int32_t* cnt, uint32_t n_rows, uint32_t n_feat, uint32_t n_trees, const uint32_t* root,
+                            const int32_t* feature, const float* value, const uint32_t* tchild, const uint32_t* fchild, const float* weight,
+                            float* score, cudaStream_t st) {
+    if (!n_rows) return 0;
+    const size_t tot = (size_t)n_rows * SHB_F_TOP * n_trees;
+    k_forest_slots<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(X, cnt, n_rows, n_feat, n_trees, root, feature, value, tchild, fchild, weight, score);
+    return 1;
+}
+int shb_launch_groove_theta_slots(const ShbRowSrc* src, int n_src, uint32_t max_rows, const double* theta, const int32_t* cnt, const float* score,
+                                  float threshold, double* bg, double* dens_max, cudaStream_t st) {
+    if (n_src <= 0) return 0;
+    const size_t smem = (size_t)max_rows * SHB_F_TOP * sizeof(double) + 16;
+    cudaFuncSetAttribute(k_groove_theta_slots, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_groove_theta_slots<<<n_src, 1024, smem, st>>>(src, theta, cnt, score, threshold, bg, dens_max);
     return 1;
 }
 }

@@ -232,25 +232,6 @@ __global__ void __launch_bounds__(256) k_frame_acc(const double4* __restrict__ v
     }
 }
 
-// eigenvectors of a symmetric 3x3 matrix by cyclic Jacobi rotations: evec columns, eval diagonal
-__device__ void shb_jacobi3(double a[3][3], double v[3][3]) {
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) v[i][j] = i == j ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 24; ++sweep) {
-        const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
-        if (off == 0.0) break;
-        for (int p = 0; p < 2; ++p)
-            for (int q = p + 1; q < 3; ++q) {
-                if (a[p][q] == 0.0) continue;
-                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
-                for (int k = 0; k < 3; ++k) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
-                for (int k = 0; k < 3; ++k) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
-                for (int k = 0; k < 3; ++k) { const double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - s * vkq; v[k][q] = s * vkp + c * vkq; }
-            }
-    }
-}
-
 template <int STAGE>
 __global__ void k_frame_step(ShbFrame* __restrict__ Fp, const double* __restrict__ part, uint32_t n_part, uint32_t V) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

@@ -86,15 +86,15 @@ def groove_points(result, sweeps, zs_list, bg_thetas, interp_num: int, deg_windo
     return [(pts[a:b], lt[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
 
 
-def neck_image(result, sweeps, bg_thetas, want_shifted: bool = False):
-    """Per listed sweep: (image float32 (rows, N) in [0, 1], (min, max), itr_shft or None)."""
+def neck_image(result, sweeps, bg_thetas, want_shifted: bool = False, interp_num: int | None = None):
+    """Per listed sweep: (image float32 (rows, N) in [0, 1], (min, max), itr_shft or None).  Pass ``interp_num`` (the N of
+    the listed sweeps): without it N is read off the itr_start array itself, which copies that whole stack to the host."""
     lib = _lib.load()
     sweeps = np.asarray(sweeps, dtype=np.int32)
     bg = np.ascontiguousarray(np.asarray(bg_thetas, dtype=np.float64))
     wins = _windows(result, sweeps, _lib.ARR_ITR_START)
     rows = [hi - lo for lo, hi in wins]
-    n = result.array(_lib.ARR_N_SEG, int(sweeps[0])).shape[0]      # noqa: F841  (forces the plane records; N comes from the window array)
-    N = result.array_shape(_lib.ARR_ITR_START, int(sweeps[0]))[2]
+    N = int(interp_num) if interp_num is not None else result.array_shape(_lib.ARR_ITR_START, int(sweeps[0]))[2]
     image = _lib.pinned_empty((sum(rows), N), np.float32)
     shft = _lib.pinned_empty((sum(rows), 2, N), np.float64) if want_shifted else None
     mm = np.zeros((len(sweeps), 2))
@@ -256,3 +256,70 @@ def detect_groove(result, sweep, zs, canal_axis, forest: Forest, interp_num: int
     bg = groove_theta(ft["peak_theta"], proba[:, 1])
     pts, local_theta = groove_points(result, [sweep], [zs], [bg], interp_num, deg_window)[0]
     return {"bg_theta": bg, "points_obb": pts, "local_theta": local_theta, "proba": proba, **ft}
+
+
+# ------------------------------------------------------------------------------------------
+# the whole front end of a batch in one enqueue (shb_landmark_front)
+# ------------------------------------------------------------------------------------------
+class _LandmarkArgs(C.Structure):
+    _fields_ = [("n_bones", C.c_int32), ("canal_lo", C.c_int32), ("canal_hi", C.c_int32),
+                ("full_sweeps", C.c_void_p), ("prox_sweeps", C.c_void_p), ("canal_z", C.c_void_p), ("canal_half", C.c_void_p),
+                ("groove_zs", C.c_void_p), ("forest", C.c_void_p), ("threshold", C.c_float), ("ivar", C.c_int32),
+                ("canal_axes", C.c_void_p), ("feat", C.c_void_p), ("peak_theta", C.c_void_p), ("peak_index", C.c_void_p),
+                ("n_peaks", C.c_void_p), ("X", C.c_void_p), ("proba1", C.c_void_p), ("scaler", C.c_void_p), ("bg_theta", C.c_void_p),
+                ("points", C.c_void_p), ("local_theta", C.c_void_p), ("image", C.c_void_p), ("minmax", C.c_void_p)]
+
+
+class LandmarkFrontEnd:
+    """Canal axis -> groove features -> StandardScaler -> forest -> groove angle -> groove points -> neck image for a batch of
+    bones whose sweeps are resident in a ``SweepResult``, in ONE device enqueue and one host wait (``shb_landmark_front``):
+    what ``canal.Canal.axis`` (canal.py:40-85), ``DeepGroove.points`` (bicipital_groove.py:94-238) and the image stage of
+    ``AnatomicNeck.points`` (anatomic_neck.py:38-58) do between ``slice.py``'s arrays and their models.  The object owns the
+    page-locked output buffers and reuses them call after call (same batch shape), so a step allocates nothing.
+
+    ``canal_rows`` = ``Slices._cutoff((0.35, 0.75))`` of the Full sweep, ``canal_z`` (n_bones, rows) the z of those planes,
+    ``canal_half`` (n_bones,) = ``obb.z_length * mean(cutoff_pcts) / 2``; ``groove_zs`` one z array per bone over the
+    ``itr_centered_start`` window of its proximal sweep."""
+
+    def __init__(self, forest: Forest, interp_num: int = 512, deg_window: float = 7, threshold: float = 0.4):
+        self.forest, self.threshold = forest, float(threshold)
+        self.ivar = max(1, int(round(deg_window / (360 / interp_num))))
+        self.interp_num = int(interp_num)
+        self._shape, self._buf = None, {}
+
+    def _buffers(self, n_bones, rows, img_rows, N):
+        shape = (n_bones, rows, img_rows, N)
+        if shape != self._shape:
+            pe = _lib.pinned_empty
+            self._buf = {"canal_axes": pe((n_bones, 2, 3), np.float64), "feat": pe((rows, N_TOP, N_FEAT), np.float64),
+                         "peak_theta": pe((rows, N_TOP), np.float64), "peak_index": pe((rows, N_TOP), np.int32), "n_peaks": pe((rows,), np.int32),
+                         "X": pe((rows, N_TOP, N_FEAT), np.float32), "proba1": pe((rows, N_TOP), np.float32), "scaler": pe((n_bones, 2, N_FEAT), np.float64),
+                         "bg_theta": pe((n_bones,), np.float64), "points": pe((rows, 3), np.float64), "local_theta": pe((rows,), np.float64),
+                         "image": pe((img_rows, N), np.float32), "minmax": pe((n_bones, 2), np.float64)}
+            self._shape = shape
+        return self._buf
+
+    def __call__(self, result, full_sweeps, prox_sweeps, canal_rows, canal_z, canal_half, groove_zs):
+        """Returns a dict of batch arrays (views of the object's buffers, valid until the next call): ``canal_axes`` (B,2,3),
+        ``feat`` / ``X`` (rows,7,9), ``peak_theta`` / ``peak_index`` / ``proba1`` (rows,7), ``n_peaks`` (rows,), ``scaler`` (B,2,9),
+        ``bg_theta`` (B,), ``points`` (rows,3), ``local_theta`` (rows,), ``image`` (image rows, N) float32, ``minmax`` (B,2), and
+        ``row_cuts`` / ``image_cuts``: the row range of bone b is ``cuts[b]:cuts[b+1]``."""
+        lib = _lib.load()
+        full = np.ascontiguousarray(full_sweeps, dtype=np.int32); prox = np.ascontiguousarray(prox_sweeps, dtype=np.int32)
+        nb = len(full)
+        cz = np.ascontiguousarray(canal_z, dtype=np.float64).reshape(nb, canal_rows[1] - canal_rows[0])
+        half = np.ascontiguousarray(canal_half, dtype=np.float64).reshape(nb)
+        zs = np.ascontiguousarray(np.concatenate([np.asarray(z, dtype=np.float64) for z in groove_zs]))
+        wins = [result.window(_lib.ARR_ITR_START, int(s)) for s in prox]
+        img_rows = [hi - lo for lo, hi in wins]
+        N = self.interp_num
+        buf = self._buffers(nb, len(zs), sum(img_rows), N)
+        a = _LandmarkArgs(nb, int(canal_rows[0]), int(canal_rows[1]), full.ctypes.data, prox.ctypes.data, cz.ctypes.data, half.ctypes.data,
+                          zs.ctypes.data, self.forest._h, self.threshold, self.ivar, *[buf[k].ctypes.data for k in
+                          ("canal_axes", "feat", "peak_theta", "peak_index", "n_peaks", "X", "proba1", "scaler", "bg_theta", "points",
+                           "local_theta", "image", "minmax")])
+        _lib.check(lib.shb_landmark_front(result._h, C.byref(a)))
+        out = dict(buf)
+        out["row_cuts"] = np.cumsum([0] + [len(z) for z in groove_zs])
+        out["image_cuts"] = np.cumsum([0] + img_rows)
+        return out

@@ -150,3 +150,73 @@ def test_device_groove_angle_equals_the_host_density_arg_max(gpu_backend):
         k = int(np.argmin(np.abs(tlin - g_)))
         assert tlin[k] == g_ and dens[k] >= dens.max() * (1 - 1e-12), (g_, r_)
     assert (got == ref).sum() >= len(ref) - 1
+
+
+@pytest.mark.gpu
+def test_fused_front_end_equals_the_step_by_step_chain(gpu_backend):
+    """shb_landmark_front (canal axis, features, StandardScaler, forest, groove angle, groove points, neck image in one
+    enqueue, everything between the stages staying on the device) against the same chain driven call by call: the canal
+    axis agrees with the host fit (numpy SVD, what scikit-spatial's Line.best_fit runs) to 1e-9 (Jacobi eigenvector against
+    LAPACK), and with that axis handed to the step-by-step chain every later result is EQUAL bit for bit — including the
+    StandardScaler, which the device sums in numpy's order."""
+    from shoulder_b200 import _lib, features
+    if not (GOLD / "forest_rfc_bg3.npz").exists():
+        pytest.skip("forest fixture missing")
+    forest = features.Forest.from_arrays(np.load(GOLD / "forest_rfc_bg3.npz"))
+    meshes, sweeps, zs_full, zs_prox = [], [], [], []
+    names = NAMES[:3]
+    nb = len(names)
+    for b, name in enumerate(names):
+        g, v, f, zs = _bone(name)
+        zf = np.linspace(0.99 * v[:, 2].max(), 0.99 * v[:, 2].min(), 200)        # FullSlices._zs
+        meshes.append((v, f))
+        sweeps += [(b, float(np.mean(zf)), zf - np.mean(zf), 100), (b, float(np.mean(zs)), zs - np.mean(zs), 512)]
+        zs_full.append(zf); zs_prox.append(zs)
+    lo, hi = oracle.cutoff_window(600, (0.2, 0.75))
+    lo2, hi2 = oracle.cutoff_window(600, (0.0, 0.852))
+    c_lo, c_hi = oracle.cutoff_window(200, (0.35, 0.75))
+    req = []
+    for b in range(nb):
+        req += [{}, {_lib.OUT_ITR_START: (lo2, hi2), _lib.OUT_ITR_CENTERED_START: (lo, hi)}]
+    res = _lib.sweep_batch(meshes, sweeps, _lib.OUT_PLANE, 0, requests=req, lazy=True)
+    full, prox = [2 * b for b in range(nb)], [2 * b + 1 for b in range(nb)]
+    half = np.array([0.55 * (abs(z[0]) + abs(z[-1])) / 2 for z in zs_full])
+    zs_g = [z[lo:hi] for z in zs_prox]
+    # ---- one call
+    fe = features.LandmarkFrontEnd(forest, 512)
+    out = fe(res, full, prox, (c_lo, c_hi), np.stack([z[c_lo:c_hi] for z in zs_full]), half, zs_g)
+    out = {k: np.array(v) for k, v in out.items()}
+    # ---- step by step
+    cz = np.stack([np.c_[res.array(_lib.ARR_CENTROID, s)[c_lo:c_hi], zs_full[b][c_lo:c_hi]] for b, s in enumerate(full)])
+    mid = cz.mean(axis=1, keepdims=True)
+    dirn = np.linalg.svd(cz - mid)[2][:, 0, :]
+    dirn = np.where(dirn[:, -1:] < 0, -dirn, dirn)
+    axes = np.stack([mid[:, 0] + dirn * half[:, None], mid[:, 0] - dirn * half[:, None]], axis=1)
+    assert np.abs(out["canal_axes"] - axes).max() < 1e-9 * np.abs(axes).max()
+    ft = features.groove_features(res, prox, zs_g, out["canal_axes"])
+    cuts = np.cumsum([0] + [len(f["X"]) for f in ft])
+    proba = forest.predict_proba(np.vstack([f["X"] for f in ft]))
+    bg = features.groove_theta_batch([f["peak_theta"] for f in ft], [proba[a:b, 1] for a, b in zip(cuts[:-1], cuts[1:])])
+    pts = features.groove_points(res, prox, zs_g, bg, 512)
+    imgs = features.neck_image(res, prox, bg, interp_num=512)
+    for b in range(nb):
+        r0, r1 = out["row_cuts"][b], out["row_cuts"][b + 1]
+        cnt = out["n_peaks"][r0:r1]
+        assert np.array_equal(cnt, ft[b]["n_peaks"])
+        sel = np.arange(features.N_TOP)[None, :] < cnt[:, None]
+        assert np.array_equal(out["peak_index"][r0:r1][sel], ft[b]["peak_index"])
+        assert np.array_equal(out["peak_theta"][r0:r1][sel], ft[b]["peak_theta"])
+        raw = out["feat"][r0:r1][sel]
+        assert np.array_equal(raw, ft[b]["raw"])
+        # StandardScaler on the device == numpy on the device's own raw rows, bit for bit
+        mean, std = raw.mean(axis=0), raw.std(axis=0)
+        std = np.where(std == 0.0, 1.0, std)
+        assert np.array_equal(out["scaler"][b, 0], mean) and np.array_equal(out["scaler"][b, 1], std)
+        assert np.array_equal(out["X"][r0:r1][sel], ((raw - mean) / std).astype(np.float32))
+        assert np.abs(out["proba1"][r0:r1][sel] - proba[cuts[b]:cuts[b + 1], 1]).max() < 1e-6      # float atomics: the trees' order
+        assert out["bg_theta"][b] == bg[b]
+        assert np.array_equal(out["points"][r0:r1], pts[b][0]) and np.array_equal(out["local_theta"][r0:r1], pts[b][1])
+        i0, i1 = out["image_cuts"][b], out["image_cuts"][b + 1]
+        assert np.array_equal(out["image"][i0:i1], imgs[b][0]) and tuple(out["minmax"][b]) == imgs[b][1]
+    res.close()
+    forest.close()
