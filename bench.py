@@ -618,22 +618,40 @@ def landmark_record(gpu: Gpu, bones: int, steps: int):
     c_lo, c_hi = int((1 - 0.75) * 200), int((1 - 0.35) * 200)
     half = np.array([0.55 * (abs(z[0]) + abs(z[-1])) / 2 for z in z_full])
 
-    fe = features.LandmarkFrontEnd(forest, 512)
-    canal_z = np.stack([z[c_lo:c_hi] for z in z_full])
+    # groups of bones in flight: group k + 1 is uploaded and swept while group k's outputs travel back (copy stream).  Measured:
+    # a group costs ~1.3 ms of host time (two host waits in create / run, ctypes, numpy), so groups under 32 bones lose more
+    # than the overlap wins (32 bones as 4 x 8: 5.4 ms against 4.2 ms in one group; 128 bones as 4 x 32: 14.7 against 16.8)
+    n_grp = max(1, min(4, bones // 32))
+    chunks, first = _lib.split_packed(packed, n_grp)
+    chunks = [tuple(gpu.torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in c) for c in chunks]
+    groups = []
+    for k, c in enumerate(chunks):
+        s0, s1 = int(first[k]), int(first[k + 1])
+        b0, b1 = s0 // 3, s1 // 3
+        groups.append({"packed": c, "req": req[s0:s1], "full": [3 * b for b in range(b1 - b0)], "prox": [3 * b + 2 for b in range(b1 - b0)],
+                       "canal_z": np.stack([z[c_lo:c_hi] for z in z_full[b0:b1]]), "half": half[b0:b1], "zs_g": zs_g[b0:b1],
+                       "fe": features.LandmarkFrontEnd(forest, 512)})
 
     def step(count=False):
-        res = _lib.sweep_batch(None, None, _lib.OUT_PLANE, 0, packed=packed, lazy=True, requests=req)
-        # ONE enqueue, one host wait (shb_landmark_front): canal axes from the plane records on the device (canal.py:40-85),
-        # groove features, StandardScaler, forest, density arg-max, groove points, neck image; then the plane records
-        out = fe(res, full, prox, (c_lo, c_hi), canal_z, half, zs_g)
-        res.fetch(_lib.OUT_PLANE)
-        out_bytes = 0
+        live = []
+        for gk in groups:
+            res = _lib.sweep_batch(None, None, _lib.OUT_PLANE, 0, packed=gk["packed"], lazy=True, requests=gk["req"])
+            # ONE enqueue, no host wait (shb_landmark_front, SHB_LF_NO_WAIT): canal axes from the plane records on the device
+            # (canal.py:40-85), groove features, StandardScaler, forest, density arg-max, groove points, neck image
+            out = gk["fe"](res, gk["full"], gk["prox"], (c_lo, c_hi), gk["canal_z"], gk["half"], gk["zs_g"], wait=False)
+            res.fetch_async(_lib.OUT_PLANE)
+            live.append((res, out))
+        out_bytes, chk = 0, 0.0
+        for res, out in live:
+            features.LandmarkFrontEnd.wait(res)
+            res.fetch(_lib.OUT_PLANE)
+            if count:
+                out_bytes += sum(out[k].nbytes for k in ("canal_axes", "feat", "peak_theta", "peak_index", "n_peaks", "proba1", "bg_theta", "points",
+                                                         "local_theta", "image", "minmax"))
+            chk += float(np.sum(out["bg_theta"])) / bones
+            res.close()
         if count:
-            out_bytes = sum(out[k].nbytes for k in ("canal_axes", "feat", "peak_theta", "peak_index", "n_peaks", "proba1", "bg_theta", "points",
-                                                    "local_theta", "image", "minmax"))
             out_bytes += 76 * sum(len(sw[2]) for sw in sweeps)                   # plane records
-        chk = float(np.mean(out["bg_theta"]))
-        res.close()
         return out_bytes, chk
 
     for _ in range(2):
@@ -649,7 +667,8 @@ def landmark_record(gpu: Gpu, bones: int, steps: int):
             "h2d_bytes_per_step": int(sum(a.nbytes for a in packed)), "d2h_bytes_per_bone": d2h / bones,
             "delivers": "per bone: plane records of the three sweeps, canal axis, groove feature rows (<= 330 x 7 x 9) + forest probabilities, "
                         "groove angle, 330 groove points, the 512 x 512 float32 neck image",
-            "call": "shoulder_b200._lib.sweep_batch(lazy, per-sweep requests) + shoulder_b200.features.LandmarkFrontEnd (shb_landmark_front: one enqueue, one host wait)",
+            "call": "per group of bones: shoulder_b200._lib.sweep_batch(lazy, per-sweep requests) + shoulder_b200.features.LandmarkFrontEnd(wait=False) "
+                    "(shb_landmark_front: one enqueue, copies on the copy stream); %d group(s) in flight" % n_grp,
             "note": "host buffers in, landmark-model inputs out; the polar stacks (4.2 + 2.7 MB per bone) never cross PCIe; mean groove angle %.6f" % chk}
 
 

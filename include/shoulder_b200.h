@@ -334,8 +334,13 @@ typedef struct shb_landmark_args {
     double* local_theta;              /* [rows] */
     float* image;                     /* [image rows][N] */
     double* minmax;                   /* [n_bones][2] */
+    uint32_t flags;                   /* SHB_LF_NO_WAIT: return once everything is enqueued (outputs must be page-locked) */
 } shb_landmark_args;
+#define SHB_LF_NO_WAIT 0x1u
 SHB_API int shb_landmark_front(shb_result* result, const shb_landmark_args* args);
+/* Waits for the outputs of shb_landmark_front(..., SHB_LF_NO_WAIT) calls on this result (their device->host copies run on the
+ * library's copy stream, so the kernels of the next batch overlap them). */
+SHB_API int shb_landmark_wait(shb_result* result);
 
 SHB_API const char* shb_last_error(void);
 SHB_API int shb_abi_version(void);

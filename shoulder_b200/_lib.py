@@ -39,6 +39,7 @@ EXPORTS = (
     "shb_mesh_create", "shb_mesh_free", "shb_mesh_transform", "shb_batch_create_on", "shb_section", "shb_ray_cast",
     "shb_groove_features", "shb_groove_points", "shb_neck_image", "shb_forest_create", "shb_forest_predict", "shb_forest_free",
     "shb_mesh_from_stl", "shb_mesh_read", "shb_groove_theta", "shb_host_alloc", "shb_host_free", "shb_landmark_front",
+    "shb_landmark_wait",
 )
 
 
@@ -88,6 +89,7 @@ def load() -> C.CDLL:
     lib.shb_forest_predict.argtypes = [p, p, i32, p]
     lib.shb_forest_free.argtypes = [p]
     lib.shb_landmark_front.argtypes = [p, p]
+    lib.shb_landmark_wait.argtypes = [p]
     lib.shb_profile_enable.argtypes = [C.c_int]
     lib.shb_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.c_int]
     lib.shb_launch_count.restype = i64

@@ -206,6 +206,7 @@ struct shb_result {
     void* h_arr[SHB_N_ARR] = {};            // six profile arrays + the radius image
     size_t esz = 8;                         // bytes per profile / radius element
     std::vector<std::vector<int64_t>> rel;  // per-sweep relative offset arrays handed out
+    std::vector<void*> lf_staged;           // pinned staging buffers of shb_landmark_front(SHB_LF_NO_WAIT) calls in flight
 };
 
 namespace {
@@ -758,6 +759,11 @@ SHB_API int shb_result_free(shb_result* r) {
     SHB_ENTER;
     if (!r) return SHB_OK;
     if (r->pending) { cudaStreamSynchronize(g.copy); r->pending = false; }
+    if (!r->lf_staged.empty()) {                             // a no-wait front end that was never waited for: its inputs may still be read
+        cudaStreamSynchronize(r->stream ? r->stream : g.stream);
+        for (void* p : r->lf_staged) pinned_put(p);
+        r->lf_staged.clear();
+    }
     cudaStream_t st = r->stream ? r->stream : g.stream;      // the stream that computed it: frees are ordered behind its kernels
     ShbDev& d = r->d;
     dfree(r->blk_keep_a, st); dfree(r->blk_keep_b, st); dfree(r->blk_tmp_a, st); dfree(r->blk_tmp_b, st);
@@ -1539,14 +1545,42 @@ SHB_API int shb_landmark_front(shb_result* r, const shb_landmark_args* a) {
     g.launches += shb_launch_neck_image(d_isrc, nb, (uint32_t)irows, iN, d_bg, reinterpret_cast<double*>(D + o_vals), nullptr,
                                         reinterpret_cast<unsigned long long*>(D + o_mm), reinterpret_cast<float*>(D + o_img), reinterpret_cast<double*>(D + o_mmo), st);
     CK(cudaGetLastError());
-    auto back = [&](void* dst, size_t o, size_t bytes) -> cudaError_t { return dst && bytes ? cudaMemcpyAsync(dst, D + o, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess; };
+    // the copies back: behind the kernels on the compute stream, or (SHB_LF_NO_WAIT) on the copy stream behind an event, so that
+    // whatever the caller enqueues next on the compute stream runs beside them
+    const bool nowait = (a->flags & SHB_LF_NO_WAIT) != 0;
+    cudaStream_t cs = st;
+    if (nowait) {
+        cudaEvent_t ev = nullptr;
+        CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CK(cudaEventRecord(ev, st));
+        CK(cudaStreamWaitEvent(g.copy, ev, 0));
+        cudaEventDestroy(ev);                                       // released once it has completed
+        cs = g.copy;
+    }
+    auto back = [&](void* dst, size_t o, size_t bytes) -> cudaError_t { return dst && bytes ? cudaMemcpyAsync(dst, D + o, bytes, cudaMemcpyDeviceToHost, cs) : cudaSuccess; };
     CK(back(a->canal_axes, o_axes, (size_t)nb * 48)); CK(back(a->feat, o_feat, G * 63 * 8)); CK(back(a->peak_theta, o_th, G * 7 * 8));
     CK(back(a->peak_index, o_idx, G * 7 * 4)); CK(back(a->n_peaks, o_cnt, G * 4)); CK(back(a->X, o_X, G * 63 * 4)); CK(back(a->proba1, o_score, G * 7 * 4));
     CK(back(a->scaler, o_stats, (size_t)nb * 18 * 8)); CK(back(a->bg_theta, o_bg, (size_t)nb * 8)); CK(back(a->points, o_pts, G * 24));
     CK(back(a->local_theta, o_lt, G * 8)); CK(back(a->image, o_img, tot * 4)); CK(back(a->minmax, o_mmo, (size_t)nb * 16));
+    if (nowait) {
+        dfree(D, cs);                                               // stream ordered: behind the copies
+        r->lf_staged.insert(r->lf_staged.end(), stg.bufs.begin(), stg.bufs.end());      // the staged inputs live until the wait
+        stg.bufs.clear();
+        r->pending = true;
+        return SHB_OK;
+    }
     CK(cudaStreamSynchronize(st));
     stg.release();
     dfree(D, st);
+    return SHB_OK;
+}
+
+SHB_API int shb_landmark_wait(shb_result* r) {
+    SHB_ENTER;
+    if (!r) return fail(SHB_E_INVALID, "null result");
+    if (r->pending) { CK(cudaStreamSynchronize(g.copy)); r->pending = false; }
+    for (void* p : r->lf_staged) pinned_put(p);
+    r->lf_staged.clear();
     return SHB_OK;
 }
 

@@ -267,7 +267,7 @@ class _LandmarkArgs(C.Structure):
                 ("groove_zs", C.c_void_p), ("forest", C.c_void_p), ("threshold", C.c_float), ("ivar", C.c_int32),
                 ("canal_axes", C.c_void_p), ("feat", C.c_void_p), ("peak_theta", C.c_void_p), ("peak_index", C.c_void_p),
                 ("n_peaks", C.c_void_p), ("X", C.c_void_p), ("proba1", C.c_void_p), ("scaler", C.c_void_p), ("bg_theta", C.c_void_p),
-                ("points", C.c_void_p), ("local_theta", C.c_void_p), ("image", C.c_void_p), ("minmax", C.c_void_p)]
+                ("points", C.c_void_p), ("local_theta", C.c_void_p), ("image", C.c_void_p), ("minmax", C.c_void_p), ("flags", C.c_uint32)]
 
 
 class LandmarkFrontEnd:
@@ -299,8 +299,11 @@ class LandmarkFrontEnd:
             self._shape = shape
         return self._buf
 
-    def __call__(self, result, full_sweeps, prox_sweeps, canal_rows, canal_z, canal_half, groove_zs):
-        """Returns a dict of batch arrays (views of the object's buffers, valid until the next call): ``canal_axes`` (B,2,3),
+    def __call__(self, result, full_sweeps, prox_sweeps, canal_rows, canal_z, canal_half, groove_zs, wait: bool = True):
+        """``wait=False`` returns once the work is enqueued (``SHB_LF_NO_WAIT``): the arrays are filled by the time
+        :meth:`wait` returns; meanwhile the next batch can be uploaded and computed (use one object per batch in flight).
+
+        Returns a dict of batch arrays (views of the object's buffers, valid until the next call): ``canal_axes`` (B,2,3),
         ``feat`` / ``X`` (rows,7,9), ``peak_theta`` / ``peak_index`` / ``proba1`` (rows,7), ``n_peaks`` (rows,), ``scaler`` (B,2,9),
         ``bg_theta`` (B,), ``points`` (rows,3), ``local_theta`` (rows,), ``image`` (image rows, N) float32, ``minmax`` (B,2), and
         ``row_cuts`` / ``image_cuts``: the row range of bone b is ``cuts[b]:cuts[b+1]``."""
@@ -317,9 +320,15 @@ class LandmarkFrontEnd:
         a = _LandmarkArgs(nb, int(canal_rows[0]), int(canal_rows[1]), full.ctypes.data, prox.ctypes.data, cz.ctypes.data, half.ctypes.data,
                           zs.ctypes.data, self.forest._h, self.threshold, self.ivar, *[buf[k].ctypes.data for k in
                           ("canal_axes", "feat", "peak_theta", "peak_index", "n_peaks", "X", "proba1", "scaler", "bg_theta", "points",
-                           "local_theta", "image", "minmax")])
+                           "local_theta", "image", "minmax")], 0 if wait else 1)
+        self._keep = (full, prox, cz, half, zs)                       # read by the enqueued copies until they are staged (the call stages them)
         _lib.check(lib.shb_landmark_front(result._h, C.byref(a)))
         out = dict(buf)
         out["row_cuts"] = np.cumsum([0] + [len(z) for z in groove_zs])
         out["image_cuts"] = np.cumsum([0] + img_rows)
         return out
+
+    @staticmethod
+    def wait(result) -> None:
+        """Blocks until the outputs of the ``wait=False`` calls on ``result`` have arrived."""
+        _lib.check(_lib.load().shb_landmark_wait(result._h))

@@ -218,5 +218,11 @@ def test_fused_front_end_equals_the_step_by_step_chain(gpu_backend):
         assert np.array_equal(out["points"][r0:r1], pts[b][0]) and np.array_equal(out["local_theta"][r0:r1], pts[b][1])
         i0, i1 = out["image_cuts"][b], out["image_cuts"][b + 1]
         assert np.array_equal(out["image"][i0:i1], imgs[b][0]) and tuple(out["minmax"][b]) == imgs[b][1]
+    # the no-wait form (copies on the library's copy stream) delivers the same bytes
+    fe2 = features.LandmarkFrontEnd(forest, 512)
+    out2 = fe2(res, full, prox, (c_lo, c_hi), np.stack([z[c_lo:c_hi] for z in zs_full]), half, zs_g, wait=False)
+    fe2.wait(res)
+    for k in ("canal_axes", "feat", "peak_theta", "peak_index", "n_peaks", "X", "scaler", "bg_theta", "points", "local_theta", "image", "minmax"):
+        assert np.array_equal(out2[k], out[k]), k
     res.close()
     forest.close()
