@@ -394,8 +394,11 @@ def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2
     # the batch is handed over as `e2e_chunks` groups of whole bones (pinned host arrays); the library overlaps
     # each group's device->host copy with the next group's upload + kernels.  Every step moves every input byte
     # host->device and every requested output byte device->host.
-    chunks, first = _lib.split_packed(packed_pinned, e2e_chunks)
-    chunks = [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in c) for c in chunks]
+    def cut(k):
+        ch, fs = _lib.split_packed(packed_pinned, k)
+        return [tuple(torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in c) for c in ch], fs
+
+    chunks, first = cut(e2e_chunks if e2e_chunks > 0 else 1)
     fetched = [_lib.ARR_N_SEG, _lib.ARR_N_ENT, _lib.ARR_STATUS, _lib.ARR_SEL, _lib.ARR_BOUNDS, _lib.ARR_CENTROID, _lib.ARR_AREA1]
     windowed = [(_lib.ARR_IXY, _lib.OUT_IXY), (_lib.ARR_ITR_START, _lib.OUT_ITR_START),
                 (_lib.ARR_ITR_CENTERED_START, _lib.OUT_ITR_CENTERED_START), (_lib.ARR_RADIAL, _lib.OUT_RADIAL)]
@@ -421,6 +424,26 @@ def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2
                         prof_elems += a.size
         return d2h, prof_elems, rad_elems
 
+    e2e_tuned = None
+    if e2e_chunks <= 0 and not single:
+        # --e2e-chunks 0: the number of groups is chosen during warm-up (a group costs ~1 ms of host time, so few-byte
+        # workloads want few groups, copy-bound ones want the first upload + sweep short): 3 untimed + 3 timed calls each
+        e2e_tuned = {}
+        for k in (1, 2, 4, 8):
+            if k > nb:
+                break
+            chunks, first = cut(k)
+            _lib.trim()                                     # the page-locked result buffers of the previous group size go back first
+            for _ in range(3):
+                e2e_call().close()
+            torch.cuda.synchronize()
+            tk = time.perf_counter()
+            for _ in range(3):
+                e2e_call().close()
+            torch.cuda.synchronize()
+            e2e_tuned[k] = gpu.reduce([(time.perf_counter() - tk) / 3 * 1e3])[0]      # every rank picks the same count
+        chunks, first = cut(min(e2e_tuned, key=e2e_tuned.get))
+        _lib.trim()
     for _ in range(max(2, warmup)):
         e2e_call().close()
     gpu.barrier()
@@ -489,7 +512,8 @@ def measure(gpu: Gpu, workload, bones, planes, interp, angles, steps, warmup, e2
                 "d2h_bytes_per_bone": d2h / max(nb, 1),
                 "outputs": ("plane records + the consumers' windows: itr_start rows 88..599 and itr_centered_start rows 150..479 of the proximal sweep, float64"
                             if requests is not None else "plane records + ixy + itr_start + itr_centered_start (+ radius image), float64, every plane"),
-                "call": f"shoulder_b200._lib.sweep_batch_pipelined, {len(chunks)} group(s) of bones"},
+                "call": f"shoulder_b200._lib.sweep_batch_pipelined, {len(chunks)} group(s) of bones"
+                        + (" (chosen in warm-up, ms per call by group count: " + ", ".join(f"{k}: {v:.2f}" for k, v in e2e_tuned.items()) + ")" if e2e_tuned else "")},
         "gpu_launches": int(launches),
     }
     if f32 is not None:
@@ -763,7 +787,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the cfg3 / cfg4 sub-records")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="groups of bones the e2e call pipelines (D2H of one overlaps compute of the next)")
+    ap.add_argument("--e2e-chunks", type=int, default=0, help="groups of bones the e2e call pipelines (D2H of one overlaps compute of the next); 0 = chosen during warm-up")
     args = ap.parse_args()
     single = args.workload.startswith("cfg3")
     if args.planes is None:
