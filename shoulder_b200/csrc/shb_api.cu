@@ -1519,6 +1519,8 @@ SHB_API int shb_landmark_front(shb_result* r, const shb_landmark_args* a) {
     CK(dalloc_bytes(reinterpret_cast<void**>(&D), off, st));
     // small inputs: one pinned staging block, one copy each (they are a few KB)
     Staging stg;
+    struct Bail { Staging& s; unsigned char*& dev; cudaStream_t st; bool armed = true;      // an early return: wait, then give back
+        ~Bail() { if (!armed) return; if (!s.bufs.empty()) { cudaStreamSynchronize(st); s.release(); } if (dev) { cudaFreeAsync(dev, st); dev = nullptr; } } } bail{stg, D, st};
     CK(stg.copy(D + o_gsrc, gsrc.data(), nb * sizeof(ShbRowSrc), st)); CK(stg.copy(D + o_isrc, isrc.data(), nb * sizeof(ShbRowSrc), st));
     CK(stg.copy(D + o_jobs, jobs.data(), nb * sizeof(ShbCanalJob), st)); CK(stg.copy(D + o_cz, a->canal_z, (size_t)nb * crow * 8, st));
     CK(stg.copy(D + o_zs, a->groove_zs, G * 8, st));
@@ -1562,6 +1564,7 @@ SHB_API int shb_landmark_front(shb_result* r, const shb_landmark_args* a) {
     CK(back(a->peak_index, o_idx, G * 7 * 4)); CK(back(a->n_peaks, o_cnt, G * 4)); CK(back(a->X, o_X, G * 63 * 4)); CK(back(a->proba1, o_score, G * 7 * 4));
     CK(back(a->scaler, o_stats, (size_t)nb * 18 * 8)); CK(back(a->bg_theta, o_bg, (size_t)nb * 8)); CK(back(a->points, o_pts, G * 24));
     CK(back(a->local_theta, o_lt, G * 8)); CK(back(a->image, o_img, tot * 4)); CK(back(a->minmax, o_mmo, (size_t)nb * 16));
+    bail.armed = false;
     if (nowait) {
         dfree(D, cs);                                               // stream ordered: behind the copies
         r->lf_staged.insert(r->lf_staged.end(), stg.bufs.begin(), stg.bufs.end());      // the staged inputs live until the wait
