@@ -81,3 +81,28 @@ def test_plane_sharding_tiles_the_sweep():
     for n, w in ((8192, 8), (600, 4), (5, 8)):
         r = [sharding.shard_planes(n, k, w) for k in range(w)]
         assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """The structs that cross the C ABI by pointer (shb_landmark_args, shb_sweep_request) as the ctypes mirrors lay them
+    out against what a C compiler makes of the header: sizes and every field offset."""
+    import ctypes
+    import shutil
+    import subprocess
+    from shoulder_b200 import features
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not found")
+    fields = [n for n, _ in features._LandmarkArgs._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "shoulder_b200.h"\nint main(void) {\n'
+                   '  printf("size %zu\\n", sizeof(shb_landmark_args));\n'
+                   + "".join(f'  printf("{f} %zu\\n", offsetof(shb_landmark_args, {f}));\n' for f in fields)
+                   + '  printf("request %zu\\n", sizeof(shb_sweep_request));\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", f"-I{ROOT / 'include'}", "-o", str(exe), str(src)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    assert int(out["size"]) == ctypes.sizeof(features._LandmarkArgs)
+    for f in fields:
+        assert int(out[f]) == getattr(features._LandmarkArgs, f).offset, f
+    req = _lib.make_requests([{}])
+    assert int(out["request"]) == ctypes.sizeof(req) // len(req)
